@@ -1,0 +1,139 @@
+"""Pin the oracle (numpy + C restatements) to the reference's own outputs.
+
+The fixtures under tests/golden/ were produced by running
+/root/reference/feature_matchers.py unmodified (tests/golden/make_golden.py).
+cv2.BFMatcher is additionally consulted live when it is importable.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, pair_goldens, golden_files
+from oracle import hamming_oracle as ho
+from oracle import c_oracle as co
+from oracle import cv2_ref
+
+RATIOS = (70, 75, 80)
+
+
+def _ids(paths):
+    return [os.path.basename(p)[:-4] for p in paths]
+
+
+def _knn_expected(g, k):
+    a = g[f"knn{k}"]
+    return a[:, :, 1], a[:, :, 3]
+
+
+@pytest.mark.parametrize("path", pair_goldens(), ids=_ids(pair_goldens()))
+def test_numpy_oracle_vs_reference_outputs(path):
+    g = load_golden(path)
+    q, t = g["query"], g["train"]
+    # the reference's own call (feature_matchers.py:39)
+    mq, mt, md = ho.reference_match(t, q)
+    assert np.array_equal(np.stack([mq, mt, md], 1), g["ref_match"][:, [0, 1, 3]])
+    assert (g["ref_match"][:, 2] == 0).all()          # imgIdx is 0 for two-matrix calls
+    for th in (30, 64):                               # feature_matchers.py:41-43
+        fq, ft, fd = ho.reference_match(t, q, dist_threshold=float(th))
+        assert np.array_equal(np.stack([fq, ft, fd], 1), g[f"ref_match_thr{th}"][:, [0, 1, 3]])
+    for k in (1, 2):
+        idx, dist = ho.knn(q, t, k)
+        eidx, edist = _knn_expected(g, k)
+        kk = min(k, t.shape[0])
+        assert np.array_equal(idx, eidx[:, :kk]) and np.array_equal(dist, edist[:, :kk])
+        assert (eidx[:, kk:] == -1).all()             # k = min(k, Nt): short rows
+    cq, ct, cd = ho.cross_check_match(q, t)
+    assert np.array_equal(np.stack([cq, ct, cd], 1), g["cross"][:, [0, 1, 3]])
+    idx, dist = ho.knn(q, t, 2)
+    for r in RATIOS:
+        keep = ho.ratio_test(idx, dist, r / 100.0)
+        got = np.stack([np.nonzero(keep)[0], idx[keep, 0], dist[keep, 0]], 1)
+        assert np.array_equal(got, g[f"ratio{r}"][:, [0, 1, 3]])
+        pq, pt, pd = ho.pipeline(q, t, ratio=r / 100.0, cross_check=True)
+        assert np.array_equal(np.stack([pq, pt, pd], 1), g[f"pipe{r}"][:, [0, 1, 3]])
+
+
+@pytest.mark.parametrize("path", pair_goldens(), ids=_ids(pair_goldens()))
+def test_c_oracle_vs_reference_outputs(path):
+    g = load_golden(path)
+    q, t = g["query"], g["train"]
+    keys = co.knn2_keys(q, t)
+    assert np.array_equal(keys, ho.knn2_keys(q, t))
+    eidx, edist = _knn_expected(g, 2)
+    idx, dist, valid = ho.keys_to_arrays(keys)
+    assert np.array_equal(np.where(valid, idx, -1), eidx)
+    assert np.array_equal(np.where(valid, dist, -1), edist)
+    for r in RATIOS:
+        pq, pt, pd = co.pipeline(q, t, ratio=r / 100.0, cross_check=True)
+        assert np.array_equal(np.stack([pq, pt, pd], 1), g[f"pipe{r}"][:, [0, 1, 3]])
+    col = co.colmin_keys(q, t)
+    d = ho.hamming_matrix(q, t)
+    assert np.array_equal(col & np.uint64(0xFFFFFFFF), np.argmin(d, axis=0).astype(np.uint64))
+
+
+def test_collection_api_golden():
+    g = load_golden(golden_files("collection_40.npz")[0])
+    sizes = g["sizes"]
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    trains = [g["train_cat"][starts[i]:starts[i + 1]] for i in range(len(sizes))]
+    img, loc, dist = ho.collection_knn(g["query"], trains, 2)
+    exp = g["knn2"]
+    assert np.array_equal(loc, exp[:, :, 1])
+    assert np.array_equal(img, exp[:, :, 2])
+    assert np.array_equal(dist, exp[:, :, 3])
+    # cross-image duplicate rows: the lower imgIdx wins
+    assert (img[:5, 0] == 0).all() and (img[:5, 1] == 3).all() and (dist[:5] == 0).all()
+
+
+def test_ratio_lut_equals_float_compare():
+    for ratio in (0.5, 0.6, 0.7, 0.75, 0.8, 0.9, 1.0, 0.123456789):
+        lut = ho.ratio_lut(ratio)
+        d1 = np.arange(257)[:, None].astype(np.float64)
+        d2 = np.arange(257)[None, :].astype(np.float64)
+        assert np.array_equal(d1 < ratio * d2, np.arange(257)[:, None] < lut[None, :])
+
+
+def test_merge_top2_equals_global():
+    rng = np.random.default_rng(5)
+    q = rng.integers(0, 256, (64, 32), dtype=np.uint8)
+    t = rng.integers(0, 4, (900, 32), dtype=np.uint8)       # tie-heavy
+    full = ho.knn2_keys(q, t)
+    for cuts in ((0, 900), (0, 1, 900), (0, 300, 301, 777, 900), (0, 450, 900)):
+        parts = [ho.knn2_keys(q, t[a:b], train_base=a) for a, b in zip(cuts[:-1], cuts[1:])]
+        assert np.array_equal(ho.merge_top2_keys(np.stack(parts)), full)
+
+
+def test_edge_shapes():
+    e32 = np.empty((0, 32), np.uint8)
+    q = np.arange(96, dtype=np.uint8).reshape(3, 32)
+    assert ho.match(e32, q)[0].size == 0
+    assert ho.match(q, e32)[0].size == 0
+    assert ho.match(np.array([]), q)[0].size == 0          # Frame.get_descriptors() with no features
+    idx, dist = ho.knn(q, e32, 2)
+    assert idx.shape == (3, 0)
+    idx, dist = ho.knn(q, q[:1], 2)
+    assert idx.shape == (3, 1)                             # k = min(k, Nt)
+    keys = ho.knn2_keys(q, q[:1])
+    assert (keys[:, 1] == ho.NO_MATCH_KEY).all()
+    assert ho.pipeline(q, q[:1])[0].size == 0              # ratio test drops rows shorter than 2
+
+
+@pytest.mark.skipif(not cv2_ref.available(), reason="cv2 not importable")
+def test_oracles_vs_cv2_live():
+    import cv2
+    rng = np.random.default_rng(11)
+    for nq, nt, hi in ((257, 513, 256), (100, 1000, 2), (64, 64, 256), (300, 2, 256)):
+        q = rng.integers(0, hi, (nq, 32), dtype=np.uint8)
+        t = rng.integers(0, hi, (nt, 32), dtype=np.uint8)
+        ref = cv2_ref.knn2_keys(q, t)
+        assert np.array_equal(ho.knn2_keys(q, t), ref)
+        assert np.array_equal(co.knn2_keys(q, t), ref)
+        for ratio in (0.7, 0.9):
+            pq, pt, pd, _ = cv2_ref.dmatches_to_arrays(cv2_ref.pipeline(q, t, ratio, True))
+            oq, ot, od = ho.pipeline(q, t, ratio, True)
+            assert np.array_equal(pq, oq) and np.array_equal(pt, ot) and np.array_equal(pd, od)
+        m = cv2_ref.ReferenceMatcher(cv2.NORM_HAMMING).match(t, q, dist_threshold=40.0)
+        mq, mt, md, _ = cv2_ref.dmatches_to_arrays(m)
+        oq, ot, od = ho.reference_match(t, q, 40.0)
+        assert np.array_equal(mq, oq) and np.array_equal(mt, ot) and np.array_equal(md, od)
