@@ -1,0 +1,151 @@
+/*
+ * hm_matcher.h - C ABI of the B200-native Hamming brute-force matcher.
+ *
+ * Drop-in boundary for ONE path of ViV99/slam-experiments: the brute-force
+ * Hamming k-nearest-neighbour matching of 256-bit ORB descriptors that
+ * /root/reference/feature_matchers.py:32-44 performs through
+ * cv2.BFMatcher(NORM_HAMMING).  The reference has no FFI of its own (it calls
+ * the opencv-python wheel), so the entry points below are what a binding for
+ * this path would bind; INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *  - plain C: pointers, sizes, no C++ types, no exceptions across the boundary;
+ *  - every function returns an hm_status (0 = ok, <0 = error);
+ *    hm_last_error() returns a thread-local description of the last failure;
+ *  - all data pointers are DEVICE pointers unless the name ends in _host;
+ *    the library never allocates or frees caller-visible memory: inputs,
+ *    outputs and workspace are caller-allocated (torch tensors in the Python
+ *    host) and nothing is retained after return;
+ *  - functions enqueue on `stream` (a cudaStream_t passed as void*, NULL =
+ *    legacy default stream) and return without synchronising;
+ *  - descriptors are rows of HM_DESC_BYTES = 32 bytes (256 bits); row strides
+ *    are in BYTES, must be multiples of 16, and base pointers 16-byte aligned;
+ *  - "query" / "train" follow cv2: bf.match(query, train).  The reference
+ *    passes its `source_descriptors` as train (feature_matchers.py:39).
+ *
+ * Result format: packed 64-bit keys
+ *      key = (uint64)distance << 32 | trainIdx          (distance in 0..256)
+ *  so that unsigned min() over keys is cv2's order: ascending distance, ties
+ *  to the lowest trainIdx (BFMatcher::knnMatchImpl, matchers.cpp; SURVEY.md
+ *  E2).  A missing neighbour (Nt < 2) is HM_NO_MATCH.
+ */
+#ifndef HM_MATCHER_H_
+#define HM_MATCHER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define HM_API __declspec(dllexport)
+#else
+#define HM_API __attribute__((visibility("default")))
+#endif
+
+#define HM_ABI_VERSION 1
+#define HM_DESC_BYTES 32
+#define HM_DESC_BITS 256
+#define HM_NO_MATCH 0xFFFFFFFFFFFFFFFFull
+/* one descriptor expanded to +/-1 int8 for the tensor-core variant */
+#define HM_PREPARED_ROW_BYTES 256
+/* prepared images are padded to whole tiles of this many rows */
+#define HM_PREPARED_TILE_ROWS 256
+
+typedef enum hm_status {
+    HM_OK = 0,
+    HM_ERR_INVALID_ARGUMENT = -1, /* cv2 raises cv2.error(-215) for these (batch_distance.cpp:274,282) */
+    HM_ERR_CUDA = -2,             /* a CUDA runtime call failed; see hm_last_error() */
+    HM_ERR_WORKSPACE = -3,        /* workspace pointer NULL or smaller than hm_workspace_bytes() */
+    HM_ERR_UNSUPPORTED = -4,      /* shape / variant outside the supported domain */
+    HM_ERR_NO_DEVICE = -5         /* no sm_100 device visible: there is NO CPU fallback */
+} hm_status;
+
+typedef enum hm_variant {
+    HM_VARIANT_AUTO = 0, /* static per-shape table baked from ncu evidence */
+    HM_VARIANT_POPC = 1, /* (a) LOP3 XOR + POPC on 32-bit words */
+    HM_VARIANT_I8 = 2    /* (b) tcgen05 kind::i8 GEMM on +/-1 expansion, H = (256 - dot) / 2 */
+} hm_variant;
+
+/* flags of hm_filter_matches / hm_match_fused */
+#define HM_FLAG_RATIO 1u          /* Lowe ratio test: keep iff d1 < ratio_lut[d2] (needs 2 neighbours) */
+#define HM_FLAG_MUTUAL 2u         /* cross-check: keep iff q is t's best query too (cv2 crossCheck=True) */
+#define HM_FLAG_DIST_THRESHOLD 4u /* reference filter: d < max(2*min_d, thr), feature_matchers.py:41-43 */
+
+/* ---- introspection ------------------------------------------------------------------ */
+HM_API int hm_version(void);
+HM_API const char* hm_last_error(void);
+/* number of SMs of the current device, or an hm_status (<0) */
+HM_API int hm_device_sm_count(void);
+/* the variant HM_VARIANT_AUTO resolves to for this shape */
+HM_API int hm_select_variant(int64_t nq, int64_t nt, int batch);
+/* scratch bytes hm_knn2* / hm_match_fused* need for this shape (variant may be AUTO) */
+HM_API size_t hm_workspace_bytes(int64_t nq, int64_t nt, int batch, int variant);
+
+/* ---- k-NN core: replaces cv2.BFMatcher.knnMatch(query, train, k=2) and, through key[0],
+ *      cv2.BFMatcher.match(query, train) = /root/reference/feature_matchers.py:39 -------- */
+/* out_keys[nq][2]; train_base is added to every trainIdx (global row id of a shard's first row) */
+HM_API int hm_knn2(const uint8_t* query, int64_t nq, int64_t q_stride,
+                   const uint8_t* train, int64_t nt, int64_t t_stride,
+                   uint64_t train_base, uint64_t* out_keys,
+                   int variant, void* workspace, size_t workspace_bytes, void* stream);
+
+/* `batch` independent problems of identical shape; problem b reads
+ * query + b*q_batch_stride and train + b*t_batch_stride (bytes) and writes
+ * out_keys[b][nq][2].  Overlapping windows are allowed (frame i+1 vs frame i of
+ * one resident sequence: /root/reference/frontend.py:185-187). */
+HM_API int hm_knn2_batched(const uint8_t* query, int64_t nq, int64_t q_stride, int64_t q_batch_stride,
+                           const uint8_t* train, int64_t nt, int64_t t_stride, int64_t t_batch_stride,
+                           int batch, uint64_t* out_keys,
+                           int variant, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- tensor-core operand preparation (resident keyframe database) --------------------- */
+/* bytes of the prepared (+/-1 int8, tiled, 128B-swizzled) image of n descriptors */
+HM_API size_t hm_prepared_bytes(int64_t n);
+/* expand n packed descriptors into `prepared` (hm_prepared_bytes(n) bytes) */
+HM_API int hm_prepare(const uint8_t* bits, int64_t n, int64_t stride, void* prepared, void* stream);
+/* k-NN over operands prepared once (train side of a keyframe database stays resident) */
+HM_API int hm_knn2_prepared(const void* query_prepared, int64_t nq,
+                            const void* train_prepared, int64_t nt,
+                            uint64_t train_base, uint64_t* out_keys,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- epilogues ------------------------------------------------------------------------ */
+/* keys[groups][rows][2] -> out_keys[rows][2]: the 2 smallest of the 2*groups candidates per row.
+ * Merges per-shard results after the all-gather of the sharded keyframe database. */
+HM_API int hm_merge_top2(const uint64_t* keys, int groups, int64_t rows, uint64_t* out_keys, void* stream);
+
+/* Ratio test / mutual check / reference distance filter + ordered compaction, per problem.
+ *  fwd_keys[batch][nq][2]  from hm_knn2*(query, train)
+ *  bwd_keys[batch][nt][2]  from hm_knn2*(train, query) (roles swapped); only read with HM_FLAG_MUTUAL
+ *  ratio_lut_host[257]     host pointer, lut[d2] = ceil(ratio * d2) in float64; only with HM_FLAG_RATIO
+ *  out_q/out_t/out_d[batch][nq] int32, ordered by queryIdx; out_count[batch]
+ */
+HM_API int hm_filter_matches(const uint64_t* fwd_keys, int64_t nq, const uint64_t* bwd_keys, int64_t nt,
+                             int batch, unsigned flags, const uint16_t* ratio_lut_host, double dist_threshold,
+                             int32_t* out_q, int32_t* out_t, int32_t* out_d, int32_t* out_count,
+                             void* stream);
+
+/* knn2 (+ the swapped pass when HM_FLAG_MUTUAL) + hm_filter_matches in one enqueue.
+ * out_keys (fwd, [batch][nq][2]) may be NULL when the caller only wants the match list. */
+HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, int64_t q_batch_stride,
+                          const uint8_t* train, int64_t nt, int64_t t_stride, int64_t t_batch_stride,
+                          int batch, unsigned flags, const uint16_t* ratio_lut_host, double dist_threshold,
+                          int32_t* out_q, int32_t* out_t, int32_t* out_d, int32_t* out_count,
+                          uint64_t* out_keys,
+                          int variant, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- host-buffer convenience (what a non-torch caller binds) --------------------------- */
+typedef struct hm_context hm_context; /* owns a stream, device scratch and pinned staging */
+HM_API int hm_context_create(hm_context** out_ctx);
+HM_API void hm_context_destroy(hm_context* ctx);
+/* numpy-in / numpy-out twin of hm_knn2: H2D, kernels, D2H, synchronises before returning */
+HM_API int hm_knn2_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
+                        const uint8_t* train_host, int64_t nt, uint64_t* out_keys_host, int variant);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HM_MATCHER_H_ */

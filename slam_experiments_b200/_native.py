@@ -1,0 +1,335 @@
+"""ctypes binding of the C ABI in include/hm_matcher.h (libhm_matcher.so).
+
+PyTorch is plumbing only: it owns device memory and streams; every argument
+that crosses the boundary is a raw pointer, a size or a stream handle.  There
+is no CPU fallback: if the library is missing or no sm_100 device is visible,
+calls raise ``NativeError``.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import threading
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libhm_matcher.so")
+
+HM_OK = 0
+VARIANT_AUTO, VARIANT_POPC, VARIANT_I8 = 0, 1, 2
+VARIANTS = {"auto": VARIANT_AUTO, "popc": VARIANT_POPC, "i8": VARIANT_I8,
+            None: VARIANT_AUTO, 0: 0, 1: 1, 2: 2}
+FLAG_RATIO, FLAG_MUTUAL, FLAG_DIST_THRESHOLD = 1, 2, 4
+NO_MATCH = 0xFFFFFFFFFFFFFFFF
+DESC_BYTES = 32
+PREPARED_ROW_BYTES = 256
+
+# every symbol include/hm_matcher.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "hm_version", "hm_last_error", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
+    "hm_knn2", "hm_knn2_batched", "hm_prepared_bytes", "hm_prepare", "hm_knn2_prepared",
+    "hm_merge_top2", "hm_filter_matches", "hm_match_fused",
+    "hm_context_create", "hm_context_destroy", "hm_knn2_host",
+)
+
+
+class NativeError(RuntimeError):
+    """The CUDA library is missing, no B200 is visible, or a native call failed."""
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def _declare(L):
+    c = ctypes
+    vp, i64, u64, sz, ci, cu = c.c_void_p, c.c_int64, c.c_uint64, c.c_size_t, c.c_int, c.c_uint
+    L.hm_version.restype = ci
+    L.hm_last_error.restype = c.c_char_p
+    L.hm_device_sm_count.restype = ci
+    L.hm_select_variant.restype = ci
+    L.hm_select_variant.argtypes = [i64, i64, ci]
+    L.hm_workspace_bytes.restype = sz
+    L.hm_workspace_bytes.argtypes = [i64, i64, ci, ci]
+    L.hm_knn2.restype = ci
+    L.hm_knn2.argtypes = [vp, i64, i64, vp, i64, i64, u64, vp, ci, vp, sz, vp]
+    L.hm_knn2_batched.restype = ci
+    L.hm_knn2_batched.argtypes = [vp, i64, i64, i64, vp, i64, i64, i64, ci, vp, ci, vp, sz, vp]
+    L.hm_prepared_bytes.restype = sz
+    L.hm_prepared_bytes.argtypes = [i64]
+    L.hm_prepare.restype = ci
+    L.hm_prepare.argtypes = [vp, i64, i64, vp, vp]
+    L.hm_knn2_prepared.restype = ci
+    L.hm_knn2_prepared.argtypes = [vp, i64, vp, i64, u64, vp, vp, sz, vp]
+    L.hm_merge_top2.restype = ci
+    L.hm_merge_top2.argtypes = [vp, ci, i64, vp, vp]
+    L.hm_filter_matches.restype = ci
+    L.hm_filter_matches.argtypes = [vp, i64, vp, i64, ci, cu, vp, c.c_double, vp, vp, vp, vp, vp]
+    L.hm_match_fused.restype = ci
+    L.hm_match_fused.argtypes = [vp, i64, i64, i64, vp, i64, i64, i64, ci, cu, vp, c.c_double,
+                                 vp, vp, vp, vp, vp, ci, vp, sz, vp]
+    L.hm_context_create.restype = ci
+    L.hm_context_create.argtypes = [c.POINTER(vp)]
+    L.hm_context_destroy.restype = None
+    L.hm_context_destroy.argtypes = [vp]
+    L.hm_knn2_host.restype = ci
+    L.hm_knn2_host.argtypes = [vp, vp, i64, vp, i64, vp, ci]
+
+
+def lib():
+    """Load libhm_matcher.so (built by ``python -m slam_experiments_b200.build``)."""
+    global _lib
+    if _lib is None:
+        with _lock:
+            if _lib is None:
+                if not os.path.exists(SO_PATH):
+                    raise NativeError(
+                        f"{SO_PATH} not found: build it with `python -m slam_experiments_b200.build` "
+                        "(there is no CPU fallback)")
+                L = ctypes.CDLL(SO_PATH)
+                _declare(L)
+                _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().hm_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != HM_OK:
+        raise NativeError(f"{what} failed with status {rc}: {last_error()}")
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise NativeError("no CUDA device visible: the Hamming matcher runs on B200 only (no CPU fallback)")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if dev.type != "cuda":
+        raise NativeError(f"device {dev} is not a CUDA device (no CPU fallback)")
+    if dev.index is None:
+        dev = torch.device("cuda", torch.cuda.current_device())
+    return dev
+
+
+def variant_id(variant) -> int:
+    try:
+        return VARIANTS[variant]
+    except KeyError:
+        raise ValueError(f"unknown variant {variant!r}; expected 'auto', 'popc' or 'i8'") from None
+
+
+# ---- workspace cache: one growing uint8 tensor per (device, stream) ---------------------------
+_ws_cache = {}
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _check_desc(t: torch.Tensor, name: str, ndim: int = 2) -> None:
+    if t.dtype != torch.uint8 or t.dim() != ndim or t.shape[-1] != DESC_BYTES or not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA uint8 tensor of shape [..., {DESC_BYTES}]")
+    if t.stride(-1) != 1 or (t.numel() and (t.stride(-2) % 16 or t.data_ptr() % 16)):
+        raise ValueError(f"{name} rows must be 16-byte aligned with unit element stride")
+
+
+def knn2_keys(query: torch.Tensor, train: torch.Tensor, train_base: int = 0, variant="auto",
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``hm_knn2``: packed top-2 keys ``[Nq, 2]`` (int64 storage of the uint64 keys)."""
+    _check_desc(query, "query")
+    _check_desc(train, "train")
+    dev = query.device
+    nq, nt = query.shape[0], train.shape[0]
+    if out is None:
+        out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
+    v = variant_id(variant)
+    L = lib()
+    with torch.cuda.device(dev):
+        wsb = L.hm_workspace_bytes(nq, nt, 1, v)
+        ws = workspace(wsb, dev)
+        check(L.hm_knn2(query.data_ptr(), nq, query.stride(0) if nq else DESC_BYTES,
+                        train.data_ptr(), nt, train.stride(0) if nt else DESC_BYTES,
+                        train_base, out.data_ptr(), v, ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "hm_knn2")
+    return out
+
+
+def knn2_keys_batched(query: torch.Tensor, train: torch.Tensor, variant="auto",
+                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``hm_knn2_batched`` over ``query[B, Nq, 32]`` and ``train[B, Nt, 32]`` (strided views allowed)."""
+    _check_desc(query, "query", 3)
+    _check_desc(train, "train", 3)
+    if query.shape[0] != train.shape[0]:
+        raise ValueError("batch sizes differ")
+    dev = query.device
+    b, nq, nt = query.shape[0], query.shape[1], train.shape[1]
+    if out is None:
+        out = torch.empty((b, nq, 2), dtype=torch.int64, device=dev)
+    v = variant_id(variant)
+    L = lib()
+    with torch.cuda.device(dev):
+        wsb = L.hm_workspace_bytes(nq, nt, b, v)
+        ws = workspace(wsb, dev)
+        check(L.hm_knn2_batched(query.data_ptr(), nq, query.stride(1) if nq else DESC_BYTES, query.stride(0),
+                                train.data_ptr(), nt, train.stride(1) if nt else DESC_BYTES, train.stride(0),
+                                b, out.data_ptr(), v, ws.data_ptr(), ws.numel(), _stream_ptr(dev)),
+              "hm_knn2_batched")
+    return out
+
+
+def prepared_bytes(n: int) -> int:
+    return int(lib().hm_prepared_bytes(n))
+
+
+def prepare(bits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``hm_prepare``: expand packed descriptors to the +/-1 int8 tensor-core image."""
+    _check_desc(bits, "bits")
+    dev = bits.device
+    n = bits.shape[0]
+    nbytes = prepared_bytes(n)
+    if out is None:
+        out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    elif out.numel() < nbytes:
+        raise ValueError("prepared buffer too small")
+    with torch.cuda.device(dev):
+        check(lib().hm_prepare(bits.data_ptr(), n, bits.stride(0) if n else DESC_BYTES, out.data_ptr(),
+                               _stream_ptr(dev)), "hm_prepare")
+    return out
+
+
+def knn2_keys_prepared(query_prepared: torch.Tensor, nq: int, train_prepared: torch.Tensor, nt: int,
+                       train_base: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    dev = query_prepared.device
+    if out is None:
+        out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
+    L = lib()
+    with torch.cuda.device(dev):
+        wsb = L.hm_workspace_bytes(nq, nt, 1, VARIANT_I8)
+        ws = workspace(wsb, dev)
+        check(L.hm_knn2_prepared(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
+                                 out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "hm_knn2_prepared")
+    return out
+
+
+def merge_top2(keys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``hm_merge_top2``: ``keys[G, rows, 2]`` -> ``[rows, 2]``."""
+    if keys.dim() != 3 or keys.shape[2] != 2 or keys.dtype != torch.int64 or not keys.is_contiguous():
+        raise ValueError("keys must be a contiguous int64 tensor [G, rows, 2]")
+    dev = keys.device
+    g, rows = keys.shape[0], keys.shape[1]
+    if out is None:
+        out = torch.empty((rows, 2), dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().hm_merge_top2(keys.data_ptr(), g, rows, out.data_ptr(), _stream_ptr(dev)), "hm_merge_top2")
+    return out
+
+
+def ratio_lut(ratio: float) -> np.ndarray:
+    """``lut[d2] = ceil(ratio * d2)`` in float64: ``d1 < ratio*d2  <=>  d1 < lut[d2]`` for integer d1."""
+    import math
+    lut = np.empty(257, dtype=np.uint16)
+    for d2 in range(257):
+        lut[d2] = min(65535, max(0, math.ceil(float(ratio) * float(d2))))
+    return lut
+
+
+def match_fused(query: torch.Tensor, train: torch.Tensor, ratio: Optional[float] = None,
+                cross_check: bool = False, dist_threshold: Optional[float] = None, variant="auto",
+                want_keys: bool = False):
+    """``hm_match_fused`` over ``[B, Nq, 32]`` / ``[B, Nt, 32]``.
+
+    Returns ``(q, t, d, count[, keys])`` device tensors; row ``b`` holds ``count[b]`` matches
+    ordered by queryIdx.
+    """
+    _check_desc(query, "query", 3)
+    _check_desc(train, "train", 3)
+    dev = query.device
+    b, nq, nt = query.shape[0], query.shape[1], train.shape[1]
+    flags = 0
+    lut_ptr = None
+    lut = None
+    if ratio is not None:
+        flags |= FLAG_RATIO
+        lut = ratio_lut(ratio)
+        lut_ptr = lut.ctypes.data
+    if cross_check:
+        flags |= FLAG_MUTUAL
+    thr = 0.0
+    if dist_threshold:
+        flags |= FLAG_DIST_THRESHOLD
+        thr = float(dist_threshold)
+    oq = torch.empty((b, nq), dtype=torch.int32, device=dev)
+    ot = torch.empty((b, nq), dtype=torch.int32, device=dev)
+    od = torch.empty((b, nq), dtype=torch.int32, device=dev)
+    cnt = torch.empty((b,), dtype=torch.int32, device=dev)
+    keys = torch.empty((b, nq, 2), dtype=torch.int64, device=dev) if want_keys else None
+    v = variant_id(variant)
+    L = lib()
+    with torch.cuda.device(dev):
+        wsb = L.hm_workspace_bytes(nq, nt, b, v)
+        ws = workspace(wsb, dev)
+        check(L.hm_match_fused(query.data_ptr(), nq, query.stride(1) if nq else DESC_BYTES, query.stride(0),
+                               train.data_ptr(), nt, train.stride(1) if nt else DESC_BYTES, train.stride(0),
+                               b, flags, lut_ptr, thr, oq.data_ptr(), ot.data_ptr(), od.data_ptr(), cnt.data_ptr(),
+                               keys.data_ptr() if keys is not None else None, v, ws.data_ptr(), ws.numel(),
+                               _stream_ptr(dev)), "hm_match_fused")
+    del lut
+    return (oq, ot, od, cnt, keys) if want_keys else (oq, ot, od, cnt)
+
+
+def sm_count() -> int:
+    n = lib().hm_device_sm_count()
+    if n < 0:
+        raise NativeError(f"hm_device_sm_count failed with status {n}: {last_error()}")
+    return n
+
+
+def select_variant(nq: int, nt: int, batch: int = 1) -> str:
+    return {VARIANT_POPC: "popc", VARIANT_I8: "i8"}[lib().hm_select_variant(nq, nt, batch)]
+
+
+def split_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """Host-side decode of packed keys: ``(idx int64, dist int32, valid bool)``."""
+    k = np.asarray(keys).view(np.uint64)
+    valid = k != np.uint64(NO_MATCH)
+    return (k & np.uint64(0xFFFFFFFF)).astype(np.int64), (k >> np.uint64(32)).astype(np.int32), valid
+
+
+class HostContext:
+    """``hm_context``: numpy in / numpy out through the C ABI alone (no torch tensors)."""
+
+    def __init__(self):
+        require_cuda()
+        self._h = ctypes.c_void_p()
+        check(lib().hm_context_create(ctypes.byref(self._h)), "hm_context_create")
+
+    def knn2_keys(self, query: np.ndarray, train: np.ndarray, variant="auto") -> np.ndarray:
+        q = np.ascontiguousarray(query, dtype=np.uint8)
+        t = np.ascontiguousarray(train, dtype=np.uint8)
+        out = np.empty((q.shape[0], 2), dtype=np.uint64)
+        check(lib().hm_knn2_host(self._h, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
+                                 out.ctypes.data, variant_id(variant)), "hm_knn2_host")
+        return out
+
+    def close(self):
+        if self._h:
+            lib().hm_context_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,435 @@
+// C ABI of the matcher (include/hm_matcher.h): argument validation, variant selection,
+// workspace carving, launch sequencing.  No CPU fallback anywhere: without an sm_100
+// device every compute entry point fails with HM_ERR_NO_DEVICE.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <mutex>
+#include <new>
+
+#include "hm_common.cuh"
+
+namespace hm {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int device_info(DeviceInfo* out)
+{
+    static std::mutex mu;
+    static DeviceInfo cache[64];
+    static bool have[64] = {false};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        set_error("no CUDA device: %s (this library has no CPU fallback)", cudaGetErrorString(e));
+        return HM_ERR_NO_DEVICE;
+    }
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev < 0 || dev >= 64) {
+        set_error("device ordinal %d out of range", dev);
+        return HM_ERR_NO_DEVICE;
+    }
+    if (!have[dev]) {
+        DeviceInfo d{};
+        d.device = dev;
+        if (cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("cudaDeviceGetAttribute failed");
+            return HM_ERR_CUDA;
+        }
+        if (d.cc_major != 10) {
+            set_error("device %d is sm_%d%d; this library is built for sm_100a only", dev, d.cc_major, d.cc_minor);
+            return HM_ERR_NO_DEVICE;
+        }
+        cache[dev] = d;
+        have[dev] = true;
+    }
+    *out = cache[dev];
+    return HM_OK;
+}
+
+namespace {
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// Static per-shape table ("variant selection"): the tensor-core variant pays an
+// operand-expansion pre-pass and needs >= 128 query rows per CTA; below ~3e7 pairs the POPC
+// kernel (one launch, train split over the grid) is launch/latency-bound and wins.
+int select_variant(long long nq, long long nt, int batch)
+{
+    const double pairs = (double)nq * (double)nt * (double)batch;
+    if (nq >= 64 && nt >= 256 && pairs >= 3.0e7) return HM_VARIANT_I8;
+    return HM_VARIANT_POPC;
+}
+
+int resolve_variant(int variant, long long nq, long long nt, int batch)
+{
+    if (variant == HM_VARIANT_AUTO) return select_variant(nq, nt, batch);
+    return variant;
+}
+
+int check_rows(const void* p, long long n, long long stride, const char* what)
+{
+    if (n < 0) {
+        set_error("%s: negative row count", what);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    if (n == 0) return HM_OK;
+    if (!p) {
+        set_error("%s: null pointer", what);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    if ((reinterpret_cast<uintptr_t>(p) & 15) || stride < HM_DESC_BYTES || (stride & 15)) {
+        set_error("%s: base must be 16-byte aligned and row stride a multiple of 16 >= 32 (got stride %lld)", what,
+                  stride);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    return HM_OK;
+}
+
+size_t knn_workspace(long long nq, long long nt, int batch, int variant, int sm_count)
+{
+    if (nq <= 0 || nt <= 0 || batch <= 0) return 0;
+    size_t a = 0, b = 0;
+    if (variant == HM_VARIANT_AUTO || variant == HM_VARIANT_POPC) a = popc_workspace_bytes(nq, nt, batch, sm_count);
+    if (variant == HM_VARIANT_AUTO || variant == HM_VARIANT_I8) b = i8_workspace_bytes(nq, nt, batch, sm_count, true);
+    return align_up(a > b ? a : b);
+}
+
+__global__ void hm_fill_keys_kernel(unsigned long long* p, long long n)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = kNoMatch;
+}
+
+int fill_no_match(unsigned long long* out, long long n, cudaStream_t stream)
+{
+    if (n <= 0) return HM_OK;
+    hm_fill_keys_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(out, n);
+    HM_CUDA_CHECK(cudaGetLastError());
+    return HM_OK;
+}
+
+int knn2_dispatch(const KnnProblem& p, unsigned long long* out, int variant, void* ws, size_t ws_bytes,
+                  cudaStream_t stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (p.batch <= 0 || p.nq == 0) return HM_OK;
+    if (!out) {
+        set_error("out_keys is null");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    if ((rc = check_rows(p.q, p.nq, p.q_stride, "query")) != HM_OK) return rc;
+    if ((rc = check_rows(p.t, p.nt, p.t_stride, "train")) != HM_OK) return rc;
+    if (p.nt == 0) return fill_no_match(out, p.nq * p.batch * 2, stream);   // knnMatch: Nq empty rows
+    if (p.batch > 1 && ((p.q_batch_stride & 15) || (p.t_batch_stride & 15))) {
+        set_error("batch strides must be multiples of 16 bytes");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    const int v = resolve_variant(variant, p.nq, p.nt, p.batch);
+    switch (v) {
+        case HM_VARIANT_POPC: return launch_popc_knn2(p, out, ws, ws_bytes, di.sm_count, stream);
+        case HM_VARIANT_I8: return launch_i8_knn2(p, out, ws, ws_bytes, di.sm_count, stream);
+        default: set_error("unknown variant %d", variant); return HM_ERR_INVALID_ARGUMENT;
+    }
+}
+
+}  // namespace
+}  // namespace hm
+
+using namespace hm;
+
+extern "C" {
+
+HM_API int hm_version(void) { return HM_ABI_VERSION; }
+
+HM_API const char* hm_last_error(void) { return g_error; }
+
+HM_API int hm_device_sm_count(void)
+{
+    DeviceInfo di;
+    const int rc = device_info(&di);
+    return rc == HM_OK ? di.sm_count : rc;
+}
+
+HM_API int hm_select_variant(int64_t nq, int64_t nt, int batch) { return select_variant(nq, nt, batch); }
+
+HM_API size_t hm_workspace_bytes(int64_t nq, int64_t nt, int batch, int variant)
+{
+    DeviceInfo di;
+    int sm = 148;   // sizing only; B200
+    if (device_info(&di) == HM_OK) sm = di.sm_count;
+    if (nq < 0 || nt < 0 || batch <= 0) return 0;
+    // fused pipeline: fwd keys + bwd keys + the larger of the two k-NN passes
+    const size_t fwd = align_up((size_t)batch * nq * 16);
+    const size_t bwd = align_up((size_t)batch * nt * 16);
+    const size_t a = knn_workspace(nq, nt, batch, variant, sm);
+    const size_t b = knn_workspace(nt, nq, batch, variant, sm);
+    return fwd + bwd + (a > b ? a : b) + 256;
+}
+
+HM_API int hm_knn2(const uint8_t* query, int64_t nq, int64_t q_stride, const uint8_t* train, int64_t nt,
+                   int64_t t_stride, uint64_t train_base, uint64_t* out_keys, int variant, void* workspace,
+                   size_t workspace_bytes, void* stream)
+{
+    KnnProblem p{};
+    p.q = query; p.t = train; p.nq = nq; p.nt = nt; p.q_stride = q_stride; p.t_stride = t_stride;
+    p.batch = 1; p.train_base = train_base;
+    return knn2_dispatch(p, reinterpret_cast<unsigned long long*>(out_keys), variant, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+HM_API int hm_knn2_batched(const uint8_t* query, int64_t nq, int64_t q_stride, int64_t q_batch_stride,
+                           const uint8_t* train, int64_t nt, int64_t t_stride, int64_t t_batch_stride, int batch,
+                           uint64_t* out_keys, int variant, void* workspace, size_t workspace_bytes, void* stream)
+{
+    KnnProblem p{};
+    p.q = query; p.t = train; p.nq = nq; p.nt = nt; p.q_stride = q_stride; p.t_stride = t_stride;
+    p.q_batch_stride = q_batch_stride; p.t_batch_stride = t_batch_stride;
+    p.batch = batch; p.train_base = 0;
+    return knn2_dispatch(p, reinterpret_cast<unsigned long long*>(out_keys), variant, workspace, workspace_bytes,
+                         static_cast<cudaStream_t>(stream));
+}
+
+HM_API size_t hm_prepared_bytes(int64_t n) { return n > 0 ? prepared_bytes(n) : 0; }
+
+HM_API int hm_prepare(const uint8_t* bits, int64_t n, int64_t stride, void* prepared, void* stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if ((rc = check_rows(bits, n, stride, "bits")) != HM_OK) return rc;
+    if (n > 0 && (!prepared || (reinterpret_cast<uintptr_t>(prepared) & 15))) {
+        set_error("prepared buffer must be non-null and 16-byte aligned");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    return launch_prepare(bits, n, stride, 0, 1, prepared, static_cast<cudaStream_t>(stream));
+}
+
+HM_API int hm_knn2_prepared(const void* query_prepared, int64_t nq, const void* train_prepared, int64_t nt,
+                            uint64_t train_base, uint64_t* out_keys, void* workspace, size_t workspace_bytes,
+                            void* stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (nq < 0 || nt < 0) {
+        set_error("negative row count");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    if (nq == 0) return HM_OK;
+    if (!out_keys) {
+        set_error("out_keys is null");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (nt == 0) return fill_no_match(reinterpret_cast<unsigned long long*>(out_keys), nq * 2, st);
+    if (!query_prepared || !train_prepared || (reinterpret_cast<uintptr_t>(query_prepared) & 15) ||
+        (reinterpret_cast<uintptr_t>(train_prepared) & 15)) {
+        set_error("prepared operands must be non-null and 16-byte aligned");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    return launch_i8_knn2_prepared(query_prepared, nq, train_prepared, nt, 1, train_base,
+                                   reinterpret_cast<unsigned long long*>(out_keys), workspace, workspace_bytes,
+                                   di.sm_count, st);
+}
+
+HM_API int hm_merge_top2(const uint64_t* keys, int groups, int64_t rows, uint64_t* out_keys, void* stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (groups <= 0 || rows < 0 || (rows > 0 && (!keys || !out_keys))) {
+        set_error("hm_merge_top2: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    return launch_merge_top2(reinterpret_cast<const unsigned long long*>(keys), groups, rows,
+                             reinterpret_cast<unsigned long long*>(out_keys), static_cast<cudaStream_t>(stream));
+}
+
+static int build_filter_args(unsigned flags, const uint16_t* ratio_lut_host, double dist_threshold, RatioLut* lut,
+                             int* thr_ceil)
+{
+    memset(lut, 0, sizeof(*lut));
+    if (flags & HM_FLAG_RATIO) {
+        if (!ratio_lut_host) {
+            set_error("HM_FLAG_RATIO needs ratio_lut_host[257]");
+            return HM_ERR_INVALID_ARGUMENT;
+        }
+        memcpy(lut->v, ratio_lut_host, sizeof(lut->v));
+    }
+    *thr_ceil = 0;
+    if (flags & HM_FLAG_DIST_THRESHOLD) {
+        // integer d < x  <=>  d < ceil(x): exact form of the reference's float compare
+        double c = ceil(dist_threshold);
+        if (!(c == c)) c = 0;                 // NaN compares false everywhere
+        if (c > 1e9) c = 1e9;
+        if (c < -1e9) c = -1e9;
+        *thr_ceil = (int)c;
+    }
+    return HM_OK;
+}
+
+HM_API int hm_filter_matches(const uint64_t* fwd_keys, int64_t nq, const uint64_t* bwd_keys, int64_t nt, int batch,
+                             unsigned flags, const uint16_t* ratio_lut_host, double dist_threshold, int32_t* out_q,
+                             int32_t* out_t, int32_t* out_d, int32_t* out_count, void* stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (batch <= 0) return HM_OK;
+    if (nq < 0 || nt < 0 || !out_count || (nq > 0 && (!fwd_keys || !out_q || !out_t || !out_d)) ||
+        ((flags & HM_FLAG_MUTUAL) && nt > 0 && !bwd_keys)) {
+        set_error("hm_filter_matches: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    RatioLut lut;
+    int thr;
+    if ((rc = build_filter_args(flags, ratio_lut_host, dist_threshold, &lut, &thr)) != HM_OK) return rc;
+    return launch_filter(reinterpret_cast<const unsigned long long*>(fwd_keys), nq,
+                         reinterpret_cast<const unsigned long long*>(bwd_keys), nt, batch, flags, lut, thr, out_q,
+                         out_t, out_d, out_count, static_cast<cudaStream_t>(stream));
+}
+
+HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, int64_t q_batch_stride,
+                          const uint8_t* train, int64_t nt, int64_t t_stride, int64_t t_batch_stride, int batch,
+                          unsigned flags, const uint16_t* ratio_lut_host, double dist_threshold, int32_t* out_q,
+                          int32_t* out_t, int32_t* out_d, int32_t* out_count, uint64_t* out_keys, int variant,
+                          void* workspace, size_t workspace_bytes, void* stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (batch <= 0) return HM_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    RatioLut lut;
+    int thr;
+    if ((rc = build_filter_args(flags, ratio_lut_host, dist_threshold, &lut, &thr)) != HM_OK) return rc;
+    const size_t need = hm_workspace_bytes(nq, nt, batch, variant);
+    if (!workspace || workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+        return HM_ERR_WORKSPACE;
+    }
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    const size_t fwd_bytes = align_up((size_t)batch * nq * 16);
+    const size_t bwd_bytes = align_up((size_t)batch * nt * 16);
+    unsigned long long* fwd = out_keys ? reinterpret_cast<unsigned long long*>(out_keys)
+                                       : reinterpret_cast<unsigned long long*>(ws);
+    unsigned long long* bwd = reinterpret_cast<unsigned long long*>(ws + fwd_bytes);
+    uint8_t* knn_ws = ws + fwd_bytes + bwd_bytes;
+    const size_t knn_ws_bytes = workspace_bytes - fwd_bytes - bwd_bytes;
+
+    KnnProblem p{};
+    p.q = query; p.t = train; p.nq = nq; p.nt = nt; p.q_stride = q_stride; p.t_stride = t_stride;
+    p.q_batch_stride = q_batch_stride; p.t_batch_stride = t_batch_stride; p.batch = batch;
+    if ((rc = knn2_dispatch(p, fwd, variant, knn_ws, knn_ws_bytes, st)) != HM_OK) return rc;
+    if ((flags & HM_FLAG_MUTUAL) && nq > 0 && nt > 0) {
+        KnnProblem r{};
+        r.q = train; r.t = query; r.nq = nt; r.nt = nq; r.q_stride = t_stride; r.t_stride = q_stride;
+        r.q_batch_stride = t_batch_stride; r.t_batch_stride = q_batch_stride; r.batch = batch;
+        if ((rc = knn2_dispatch(r, bwd, variant, knn_ws, knn_ws_bytes, st)) != HM_OK) return rc;
+    }
+    if (!out_count || (nq > 0 && (!out_q || !out_t || !out_d))) {
+        set_error("hm_match_fused: null output");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    return launch_filter(fwd, nq, bwd, nt, batch, flags, lut, thr, out_q, out_t, out_d, out_count, st);
+}
+
+// ---- host-buffer convenience ---------------------------------------------------------------
+struct hm_context {
+    cudaStream_t stream;
+    uint8_t* d_buf;      // device: [query | train | keys | workspace]
+    size_t d_cap;
+    uint8_t* h_buf;      // pinned staging, same carving for query | train | keys
+    size_t h_cap;
+};
+
+HM_API int hm_context_create(hm_context** out_ctx)
+{
+    if (!out_ctx) {
+        set_error("out_ctx is null");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    hm_context* c = new (std::nothrow) hm_context();
+    if (!c) {
+        set_error("out of host memory");
+        return HM_ERR_CUDA;
+    }
+    memset(c, 0, sizeof(*c));
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        set_error("cudaStreamCreate failed: %s", cudaGetErrorString(e));
+        delete c;
+        return HM_ERR_CUDA;
+    }
+    *out_ctx = c;
+    return HM_OK;
+}
+
+HM_API void hm_context_destroy(hm_context* ctx)
+{
+    if (!ctx) return;
+    if (ctx->d_buf) cudaFree(ctx->d_buf);
+    if (ctx->h_buf) cudaFreeHost(ctx->h_buf);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+HM_API int hm_knn2_host(hm_context* ctx, const uint8_t* query_host, int64_t nq, const uint8_t* train_host, int64_t nt,
+                        uint64_t* out_keys_host, int variant)
+{
+    if (!ctx || nq < 0 || nt < 0 || (nq > 0 && (!query_host || !out_keys_host)) || (nt > 0 && !train_host)) {
+        set_error("hm_knn2_host: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    if (nq == 0) return HM_OK;
+    const size_t qb = align_up((size_t)nq * HM_DESC_BYTES, 1024), tb = align_up((size_t)nt * HM_DESC_BYTES, 1024);
+    const size_t kb = align_up((size_t)nq * 16, 1024);
+    const size_t wsb = align_up(hm_workspace_bytes(nq, nt, 1, variant), 1024);
+    const size_t dneed = qb + tb + kb + wsb, hneed = qb + tb + kb;
+    if (ctx->d_cap < dneed) {
+        if (ctx->d_buf) cudaFree(ctx->d_buf);
+        ctx->d_buf = nullptr; ctx->d_cap = 0;
+        HM_CUDA_CHECK(cudaMalloc(&ctx->d_buf, dneed));
+        ctx->d_cap = dneed;
+    }
+    if (ctx->h_cap < hneed) {
+        if (ctx->h_buf) cudaFreeHost(ctx->h_buf);
+        ctx->h_buf = nullptr; ctx->h_cap = 0;
+        HM_CUDA_CHECK(cudaMallocHost(&ctx->h_buf, hneed));
+        ctx->h_cap = hneed;
+    }
+    uint8_t *dq = ctx->d_buf, *dt = dq + qb, *dk = dt + tb, *dw = dk + kb;
+    uint8_t *hq = ctx->h_buf, *ht = hq + qb, *hk = ht + tb;
+    memcpy(hq, query_host, (size_t)nq * HM_DESC_BYTES);
+    if (nt) memcpy(ht, train_host, (size_t)nt * HM_DESC_BYTES);
+    HM_CUDA_CHECK(cudaMemcpyAsync(dq, hq, (size_t)nq * HM_DESC_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    if (nt) HM_CUDA_CHECK(cudaMemcpyAsync(dt, ht, (size_t)nt * HM_DESC_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = hm_knn2(dq, nq, HM_DESC_BYTES, dt, nt, HM_DESC_BYTES, 0, reinterpret_cast<uint64_t*>(dk), variant, dw, wsb,
+                     ctx->stream);
+    if (rc != HM_OK) return rc;
+    HM_CUDA_CHECK(cudaMemcpyAsync(hk, dk, (size_t)nq * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    memcpy(out_keys_host, hk, (size_t)nq * 16);
+    return HM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+// Shared device/host helpers for the Hamming matcher kernels (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "hm_matcher.h"
+
+namespace hm {
+
+constexpr unsigned long long kNoMatch = 0xFFFFFFFFFFFFFFFFull;
+
+// thread-local error string behind hm_last_error()
+void set_error(const char* fmt, ...);
+
+#define HM_CUDA_CHECK(expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            hm::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),        \
+                          __FILE__, __LINE__);                                           \
+            return HM_ERR_CUDA;                                                          \
+        }                                                                                \
+    } while (0)
+
+// One k-NN problem family: `batch` problems of identical shape.
+struct KnnProblem {
+    const uint8_t* q;
+    const uint8_t* t;
+    long long nq, nt;
+    long long q_stride, t_stride;             // bytes between rows
+    long long q_batch_stride, t_batch_stride; // bytes between problems
+    int batch;
+    unsigned long long train_base;            // added to every trainIdx
+};
+
+struct DeviceInfo {
+    int device;
+    int sm_count;
+    int cc_major, cc_minor;
+};
+// cached per device; returns an hm_status
+int device_info(DeviceInfo* out);
+
+inline __host__ __device__ long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
+
+// insert `key` into the ascending pair (k1, k2)
+__device__ __forceinline__ void top2_insert(unsigned long long& k1, unsigned long long& k2,
+                                            unsigned long long key)
+{
+    unsigned long long hi = key > k1 ? key : k1;
+    k1 = key < k1 ? key : k1;
+    k2 = hi < k2 ? hi : k2;
+}
+
+// ---- launchers implemented in the .cu files -------------------------------------------
+// (a) POPC variant.  partial == nullptr -> writes final keys to out.
+int popc_splits(const KnnProblem& p, int sm_count);
+int launch_popc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes,
+                     int sm_count, cudaStream_t stream);
+size_t popc_workspace_bytes(long long nq, long long nt, int batch, int sm_count);
+
+// (b) tcgen05 kind::i8 variant.
+size_t prepared_bytes(long long n);
+int launch_prepare(const uint8_t* bits, long long n, long long stride, long long batch_stride, int batch,
+                   void* prepared, cudaStream_t stream);
+int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
+                            unsigned long long train_base, unsigned long long* out, void* ws,
+                            size_t ws_bytes, int sm_count, cudaStream_t stream);
+size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare);
+int launch_i8_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count,
+                   cudaStream_t stream);
+
+// epilogues
+int launch_merge_top2(const unsigned long long* keys, int groups, long long rows, unsigned long long* out,
+                      cudaStream_t stream);
+
+struct RatioLut {
+    unsigned short v[257];
+};
+int launch_filter(const unsigned long long* fwd, long long nq, const unsigned long long* bwd, long long nt,
+                  int batch, unsigned flags, const RatioLut& lut, int thr_ceil, int* out_q, int* out_t,
+                  int* out_d, int* out_count, cudaStream_t stream);
+
+}  // namespace hm

@@ -1,0 +1,156 @@
+// Epilogues over packed top-2 keys: shard/split merge, Lowe ratio test, mutual
+// cross-check, the reference's distance filter, ordered stream compaction.
+//
+//  - merge: top-k of a union = top-k of the per-set top-k's;
+//    unsigned min over (dist << 32 | idx) is cv2's tie order.
+//  - ratio: integer LUT form of `m.distance < ratio * n.distance` (float64 on the
+//    host, see oracle/hamming_oracle.py:ratio_lut) so bit-exactness never depends
+//    on GPU floating point.
+//  - mutual: cv2.BFMatcher(crossCheck=True).match == strict mutual NN with
+//    lowest-index ties both ways; the reverse pass is a k-NN with
+//    roles swapped.
+//  - distance filter: /root/reference/feature_matchers.py:41-43,
+//    keep d < max(2 * min_d, dist_threshold) (strict).
+#include "hm_common.cuh"
+
+namespace hm {
+
+namespace {
+
+__global__ void __launch_bounds__(256) hm_merge_top2_kernel(const unsigned long long* __restrict__ keys,
+                                                            int groups, long long rows,
+                                                            unsigned long long* __restrict__ out)
+{
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    unsigned long long k1 = kNoMatch, k2 = kNoMatch;
+    for (int g = 0; g < groups; ++g) {
+        const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(keys + ((long long)g * rows + r) * 2);
+        top2_insert(k1, k2, k.x);
+        top2_insert(k1, k2, k.y);
+    }
+    *reinterpret_cast<ulonglong2*>(out + r * 2) = make_ulonglong2(k1, k2);
+}
+
+constexpr int kFilterThreads = 1024;
+
+struct FilterParams {
+    const unsigned long long* fwd;
+    const unsigned long long* bwd;
+    long long nq, nt;
+    unsigned flags;
+    int thr_ceil;                    // ceil(dist_threshold), exact integer form of the float compare
+    int* out_q;
+    int* out_t;
+    int* out_d;
+    int* out_count;
+    RatioLut lut;
+};
+
+// One CTA per problem: rows are visited in order so the output stays sorted by queryIdx.
+__global__ void __launch_bounds__(kFilterThreads) hm_filter_kernel(const FilterParams P)
+{
+    __shared__ int warp_sums[32];
+    __shared__ int s_base;
+    __shared__ unsigned s_min;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int b = blockIdx.x;
+    const unsigned long long* fwd = P.fwd + (long long)b * P.nq * 2;
+    const unsigned long long* bwd = P.bwd ? P.bwd + (long long)b * P.nt * 2 : nullptr;
+    int* oq = P.out_q + (long long)b * P.nq;
+    int* ot = P.out_t + (long long)b * P.nq;
+    int* od = P.out_d + (long long)b * P.nq;
+
+    int limit = 0x7FFFFFFF;
+    if (P.flags & HM_FLAG_DIST_THRESHOLD) {
+        if (tid == 0) s_min = 0xFFFFFFFFu;
+        __syncthreads();
+        unsigned m = 0xFFFFFFFFu;
+        for (long long r = tid; r < P.nq; r += kFilterThreads) {
+            const unsigned long long k1 = fwd[r * 2];
+            if (k1 != kNoMatch) m = min(m, (unsigned)(k1 >> 32));
+        }
+        for (int o = 16; o; o >>= 1) m = min(m, __shfl_xor_sync(0xFFFFFFFFu, m, o));
+        if (lane == 0) atomicMin(&s_min, m);
+        __syncthreads();
+        const unsigned mn = s_min;
+        limit = mn == 0xFFFFFFFFu ? 0 : max((int)(2 * mn), P.thr_ceil);
+    }
+    if (tid == 0) s_base = 0;
+    __syncthreads();
+
+    for (long long r0 = 0; r0 < P.nq; r0 += kFilterThreads) {
+        const long long r = r0 + tid;
+        int keep = 0, t1 = 0, d1 = 0;
+        if (r < P.nq) {
+            const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(fwd + r * 2);
+            keep = k.x != kNoMatch;
+            t1 = (int)(unsigned)(k.x & 0xFFFFFFFFull);
+            d1 = (int)(k.x >> 32);
+            if (keep && (P.flags & HM_FLAG_RATIO)) {
+                keep = (k.y != kNoMatch) && d1 < (int)P.lut.v[min((unsigned)(k.y >> 32), 256u)];
+            }
+            if (keep && (P.flags & HM_FLAG_MUTUAL)) {
+                keep = (long long)(bwd[(long long)t1 * 2] & 0xFFFFFFFFull) == r;
+            }
+            if (keep && (P.flags & HM_FLAG_DIST_THRESHOLD)) keep = d1 < limit;
+        }
+        // ordered block scan of the keep flags
+        const unsigned ballot = __ballot_sync(0xFFFFFFFFu, keep);
+        const int prefix = __popc(ballot & ((1u << lane) - 1));
+        if (lane == 0) warp_sums[wid] = __popc(ballot);
+        __syncthreads();
+        int wbase = 0, total = 0;
+        {
+            int v = lane < (kFilterThreads / 32) ? warp_sums[lane] : 0;
+            int incl = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                int n = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                if (lane >= o) incl += n;
+            }
+            wbase = __shfl_sync(0xFFFFFFFFu, incl - v, wid);
+            total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        }
+        const int base = s_base;
+        if (keep) {
+            const int pos = base + wbase + prefix;
+            oq[pos] = (int)r;
+            ot[pos] = t1;
+            od[pos] = d1;
+        }
+        __syncthreads();
+        if (tid == 0) s_base = base + total;
+        __syncthreads();
+    }
+    if (tid == 0) P.out_count[b] = s_base;
+}
+
+}  // namespace
+
+int launch_merge_top2(const unsigned long long* keys, int groups, long long rows, unsigned long long* out,
+                      cudaStream_t stream)
+{
+    if (rows <= 0) return HM_OK;
+    const int threads = 256;
+    const long long blocks = ceil_div(rows, threads);
+    hm_merge_top2_kernel<<<(unsigned)blocks, threads, 0, stream>>>(keys, groups, rows, out);
+    HM_CUDA_CHECK(cudaGetLastError());
+    return HM_OK;
+}
+
+int launch_filter(const unsigned long long* fwd, long long nq, const unsigned long long* bwd, long long nt,
+                  int batch, unsigned flags, const RatioLut& lut, int thr_ceil, int* out_q, int* out_t,
+                  int* out_d, int* out_count, cudaStream_t stream)
+{
+    if (batch <= 0) return HM_OK;
+    FilterParams P{};
+    P.fwd = fwd; P.bwd = bwd; P.nq = nq; P.nt = nt; P.flags = flags;
+    P.out_q = out_q; P.out_t = out_t; P.out_d = out_d; P.out_count = out_count;
+    P.lut = lut;
+    P.thr_ceil = thr_ceil;
+    hm_filter_kernel<<<batch, kFilterThreads, 0, stream>>>(P);
+    HM_CUDA_CHECK(cudaGetLastError());
+    return HM_OK;
+}
+
+}  // namespace hm

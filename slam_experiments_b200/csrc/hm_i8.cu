@@ -1,0 +1,439 @@
+// Variant (b): tcgen05 kind::i8 GEMM on the +/-1 expansion of the descriptors.
+//
+// dot(a, b) over the +/-1 int8 images of two 256-bit descriptors is 256 - 2*H, so the
+// exact Hamming distance is H = (256 - dot) / 2 and "nearest" is "largest dot".  One
+// CTA owns a 128-query block (A operand, resident in shared memory) and streams
+// 256-row train tiles (B operand) through a bulk-async-copy ring; a single elected
+// thread issues 8 x tcgen05.mma (M=128, N=256, K=32 bytes) per tile into one of two
+// 256-column TMEM accumulators; four epilogue warps read the other accumulator with
+// tcgen05.ld (thread = query row, registers = train columns) and keep the running
+// top-2 in registers, so the 128x256 distance tile never leaves the SM.
+//
+// Replaces the same cv::batchDistance loop as hm_popc.cu
+// (/root/reference/feature_matchers.py:39 -> cv2.BFMatcher).
+//
+// Operands are "prepared" once by hm_prepare(): 256 bytes per descriptor, grouped in
+// blocks of 128 rows x 128 bytes (one K slab) laid out exactly as the UMMA K-major
+// SWIZZLE_128B shared-memory image, so a block is one contiguous 16 KB bulk copy
+// (cp.async.bulk / UBLKCP) with no tensor map.
+#include "hm_common.cuh"
+#include "hm_tcgen05.cuh"
+
+namespace hm {
+
+namespace {
+
+constexpr int kBlockM = 128;                 // queries per CTA
+constexpr int kBlockN = 256;                 // train rows per tile
+constexpr int kRowBlock = 128;               // rows per prepared block
+constexpr int kSlabBytes = kRowBlock * 128;  // 16 KB: 128 rows x 128 bytes of K
+constexpr int kRowBlockBytes = 2 * kSlabBytes;
+constexpr int kPadRows = HM_PREPARED_TILE_ROWS;
+constexpr int kStages = 2;
+constexpr int kABytes = 2 * kSlabBytes;      // 32 KB
+constexpr int kBStageBytes = 4 * kSlabBytes; // 64 KB
+constexpr int kTmemCols = 512;
+constexpr int kThreads = 192;                // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+constexpr int kSmemBytes = 1024 + kABytes + kStages * kBStageBytes + 256;
+constexpr uint32_t kSpinLimit = 1u << 26;
+
+static_assert(kPadRows % kBlockN == 0 && kPadRows % kBlockM == 0, "prepared padding must cover whole tiles");
+
+// ------------------------------------------------------------------------------------------
+// hm_prepare: packed bits -> +/-1 int8 in the tiled swizzled layout.  One thread writes one
+// 16-byte chunk (16 descriptor bits); consecutive threads write consecutive chunks.
+// ------------------------------------------------------------------------------------------
+struct PrepareParams {
+    const uint8_t* bits;
+    long long n, stride, batch_stride;
+    long long padded_rows;
+    uint8_t* out;
+};
+
+__global__ void __launch_bounds__(256) hm_prepare_kernel(const PrepareParams P)
+{
+    const long long chunks_per_problem = P.padded_rows * 16;
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= chunks_per_problem) return;
+    const int b = blockIdx.y;
+    const long long rb = o >> 11;            // 2048 chunks per 128-row block
+    const int rem = (int)(o & 2047);
+    const int slab = rem >> 10;
+    const int rem2 = rem & 1023;
+    const int rr = (rem2 >> 3) & 7;          // row within its 8-row group
+    const int r = ((rem2 >> 6) << 3) | rr;   // row within the block
+    const int c = (rem2 & 7) ^ rr;           // logical 16-byte chunk stored at this position
+    const long long row = rb * kRowBlock + r;
+    uint4 v = make_uint4(0, 0, 0, 0);        // padding rows stay zero
+    if (row < P.n) {
+        const uint8_t* src = P.bits + (long long)b * P.batch_stride + row * P.stride + slab * 16 + c * 2;
+        const unsigned bits16 = (unsigned)src[0] | ((unsigned)src[1] << 8);
+        unsigned w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const unsigned nib = (bits16 >> (4 * i)) & 0xF;
+            const unsigned spread = (nib & 1) | ((nib & 2) << 7) | ((nib & 4) << 14) | ((nib & 8) << 21);
+            w[i] = (spread * 0xFEu) ^ 0xFFFFFFFFu;   // bit 1 -> 0x01 (+1), bit 0 -> 0xFF (-1)
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(P.out + (long long)b * P.padded_rows * HM_PREPARED_ROW_BYTES);
+    dst[o] = v;
+}
+
+// ------------------------------------------------------------------------------------------
+// main kernel
+// ------------------------------------------------------------------------------------------
+struct I8Params {
+    const uint8_t* qprep;            // [batch][q_padded][256]
+    const uint8_t* tprep;            // [batch][t_padded][256]
+    long long nq, nt;
+    long long q_padded, t_padded;
+    int tiles_per_split;             // train tiles (256 rows) per split
+    int ntiles;                      // total train tiles
+    unsigned long long train_base;
+    unsigned long long* out;         // [split][batch][nq][2]
+    long long out_split_stride;      // keys
+    int* error_flag;
+};
+
+struct Top2 {
+    int v1, v2;                      // best / second-best dot (larger = closer)
+    unsigned i1, i2;                 // train row local to this CTA's range
+};
+
+__device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity, int* error_flag)
+{
+    uint32_t spins = 0;
+    while (!ptx::mbar_try_wait(bar, parity)) {
+        if (++spins > kSpinLimit) {          // a protocol bug must not hang the GPU
+            if (error_flag) atomicExch(error_flag, 1);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32])
+{
+    // wait for the asynchronous register writes of tcgen05.ld; the "+r" operands pin the
+    // ordering of every later use of r[] after this point
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
+                   "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
+                   "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
+                   "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// 32 consecutive train columns of one query row.  Fast path: one 3-input-max tree per 8
+// columns against the running second best; the exact (value, index) insertion only runs for
+// groups that can change the top-2.  Strict '>' keeps the lowest train index on ties because
+// columns are visited in ascending order.
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], unsigned colbase, unsigned limit, Top2& s)
+{
+#pragma unroll
+    for (int g = 0; g < 32; g += 8) {
+        const int m = __vimax3_s32(__vimax3_s32((int)r[g], (int)r[g + 1], (int)r[g + 2]),
+                                   __vimax3_s32((int)r[g + 3], (int)r[g + 4], (int)r[g + 5]),
+                                   max((int)r[g + 6], (int)r[g + 7]));
+        if (m > s.v2) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int x = (int)r[g + e];
+                const unsigned idx = colbase + g + e;
+                if (x > s.v2 && idx < limit) {
+                    if (x > s.v1) {
+                        s.v2 = s.v1; s.i2 = s.i1;
+                        s.v1 = x;    s.i1 = idx;
+                    } else {
+                        s.v2 = x;    s.i2 = idx;
+                    }
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params P)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kABytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + kStages * kBStageBytes);
+    uint64_t* full_bar = bars;                   // [kStages]  bulk copies landed
+    uint64_t* empty_bar = bars + kStages;        // [kStages]  MMAs reading the stage retired
+    uint64_t* a_full_bar = bars + 2 * kStages;   // [1]
+    uint64_t* tmem_full_bar = bars + 2 * kStages + 1;   // [2] accumulator complete
+    uint64_t* tmem_empty_bar = bars + 2 * kStages + 3;  // [2] accumulator drained by the epilogue
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int qb = blockIdx.x;
+    const int split = blockIdx.y;
+    const int b = blockIdx.z;
+
+    const int tile_begin = split * P.tiles_per_split;
+    const int tile_end = min(tile_begin + P.tiles_per_split, P.ntiles);
+    const int my_tiles = tile_end - tile_begin;          // >= 1 by construction
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < kStages; ++i) {
+            ptx::mbar_init(&full_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], 1);
+        }
+        ptx::mbar_init(a_full_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&tmem_full_bar[i], 1);
+            ptx::mbar_init(&tmem_empty_bar[i], 4);       // one arrival per epilogue warp
+        }
+        ptx::fence_barrier_init();
+        ptx::fence_proxy_async();
+    } else if (warp == 1) {
+        ptx::tmem_alloc(tmem_base_slot, kTmemCols);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_slot;
+
+    if (warp == 0) {
+        // ===== producer: bulk async copies global -> shared =====
+        if (lane == 0) {
+            const uint8_t* qsrc = P.qprep + ((long long)b * P.q_padded + (long long)qb * kBlockM) * HM_PREPARED_ROW_BYTES;
+            ptx::mbar_arrive_expect_tx(a_full_bar, kABytes);
+            ptx::bulk_g2s(smem_a, qsrc, kABytes, a_full_bar);          // [slab0 | slab1] of one row block
+            const uint8_t* tsrc = P.tprep + (long long)b * P.t_padded * HM_PREPARED_ROW_BYTES;
+            for (int i = 0; i < my_tiles; ++i) {
+                const int stage = i % kStages;
+                const uint32_t use = i / kStages;
+                bounded_wait(&empty_bar[stage], (use & 1) ^ 1, P.error_flag);
+                ptx::mbar_arrive_expect_tx(&full_bar[stage], kBStageBytes);
+                uint8_t* dst = smem_b + stage * kBStageBytes;
+                const uint8_t* src = tsrc + (long long)(tile_begin + i) * 2 * kRowBlockBytes;
+                // stage image: [slab0: rows 0-127 | rows 128-255][slab1: rows 0-127 | rows 128-255]
+                ptx::bulk_g2s(dst,                  src,                               kSlabBytes, &full_bar[stage]);
+                ptx::bulk_g2s(dst + kSlabBytes,     src + kRowBlockBytes,              kSlabBytes, &full_bar[stage]);
+                ptx::bulk_g2s(dst + 2 * kSlabBytes, src + kSlabBytes,                  kSlabBytes, &full_bar[stage]);
+                ptx::bulk_g2s(dst + 3 * kSlabBytes, src + kRowBlockBytes + kSlabBytes, kSlabBytes, &full_bar[stage]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        constexpr uint32_t idesc = ptx::make_i8_idesc(kBlockM, kBlockN);
+        const uint32_t a_addr = ptx::smem_u32(smem_a);
+        const uint32_t b_addr = ptx::smem_u32(smem_b);
+        bounded_wait(a_full_bar, 0, P.error_flag);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int stage = i % kStages;
+            const uint32_t use = i / kStages;
+            const int acc = i & 1;
+            const uint32_t acc_use = i >> 1;
+            bounded_wait(&tmem_empty_bar[acc], (acc_use & 1) ^ 1, P.error_flag);
+            bounded_wait(&full_bar[stage], use & 1, P.error_flag);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + s * kSlabBytes + k * 32);
+                        const uint64_t db = ptx::make_kmajor_sw128_desc(b_addr + stage * kBStageBytes +
+                                                                        s * 2 * kSlabBytes + k * 32);
+                        ptx::mma_i8_ss(tmem_base + acc * kBlockN, da, db, idesc, (s | k) != 0);
+                    }
+                }
+                ptx::tc_commit(&empty_bar[stage]);        // smem stage reusable once these MMAs retire
+                ptx::tc_commit(&tmem_full_bar[acc]);      // accumulator ready for the epilogue
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===== epilogue: TMEM -> registers, running top-2 per query row =====
+        const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
+        const long long row = (long long)qb * kBlockM + quarter * 32 + lane;
+        Top2 s;
+        s.v1 = s.v2 = INT_MIN;
+        s.i1 = s.i2 = 0;
+        const long long first_row = (long long)tile_begin * kBlockN;
+        const unsigned limit = (unsigned)min((long long)my_tiles * kBlockN, P.nt - first_row);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int acc = i & 1;
+            const uint32_t acc_use = i >> 1;
+            bounded_wait(&tmem_full_bar[acc], acc_use & 1, P.error_flag);
+            ptx::tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN;
+            const unsigned colbase = (unsigned)i * kBlockN;
+            uint32_t ra[32], rb[32];
+            ptx::tmem_ld_32x32(taddr, ra);
+#pragma unroll
+            for (int c = 0; c < kBlockN / 32; c += 2) {
+                tmem_ld_fence(ra);
+                ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
+                scan_chunk(ra, colbase + c * 32, limit, s);
+                tmem_ld_fence(rb);
+                if (c + 2 < kBlockN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+                scan_chunk(rb, colbase + (c + 1) * 32, limit, s);
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        if (row < P.nq) {
+            const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
+            ulonglong2 k;
+            k.x = s.v1 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v1) >> 1) << 32) | (gbase + s.i1);
+            k.y = s.v2 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v2) >> 1) << 32) | (gbase + s.i2);
+            unsigned long long* out = P.out + (long long)split * P.out_split_stride + ((long long)b * P.nq + row) * 2;
+            *reinterpret_cast<ulonglong2*>(out) = k;
+        }
+    }
+
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+struct I8Plan {
+    int ntiles, splits, tiles_per_split;
+    long long qblocks;
+};
+
+I8Plan plan_i8(long long nq, long long nt, int batch, int sm_count)
+{
+    I8Plan pl{};
+    pl.qblocks = ceil_div(nq, kBlockM);
+    pl.ntiles = (int)ceil_div(nt, kBlockN);
+    const long long items = pl.qblocks * batch;
+    // choose the split count minimising (waves) x (tiles per CTA + fixed prologue of ~2 tiles)
+    long long best_cost = -1;
+    int best = 1;
+    const int max_splits = (int)min((long long)pl.ntiles, 4096ll);
+    for (int s = 1; s <= max_splits; ++s) {
+        const long long tps = ceil_div(pl.ntiles, s);
+        const long long real_s = ceil_div(pl.ntiles, tps);
+        const long long waves = ceil_div(items * real_s, sm_count);
+        const long long cost = waves * (tps + 2);
+        if (best_cost < 0 || cost < best_cost) {
+            best_cost = cost;
+            best = s;
+        }
+        if (items * s > 16ll * sm_count) break;
+    }
+    pl.tiles_per_split = (int)ceil_div(pl.ntiles, best);
+    pl.splits = (int)ceil_div(pl.ntiles, pl.tiles_per_split);
+    return pl;
+}
+
+long long padded_rows(long long n) { return ceil_div(n, kPadRows) * kPadRows; }
+
+}  // namespace
+
+size_t prepared_bytes(long long n) { return (size_t)padded_rows(n) * HM_PREPARED_ROW_BYTES; }
+
+int launch_prepare(const uint8_t* bits, long long n, long long stride, long long batch_stride, int batch,
+                   void* prepared, cudaStream_t stream)
+{
+    if (n <= 0 || batch <= 0) return HM_OK;
+    PrepareParams P{};
+    P.bits = bits; P.n = n; P.stride = stride; P.batch_stride = batch_stride;
+    P.padded_rows = padded_rows(n);
+    P.out = static_cast<uint8_t*>(prepared);
+    const long long chunks = P.padded_rows * 16;
+    dim3 grid((unsigned)ceil_div(chunks, 256), (unsigned)batch);
+    hm_prepare_kernel<<<grid, 256, 0, stream>>>(P);
+    HM_CUDA_CHECK(cudaGetLastError());
+    return HM_OK;
+}
+
+// workspace layout: [error flag 256 B][partials][prepared q][prepared t]
+static size_t i8_partials_bytes(long long nq, long long nt, int batch, int sm_count)
+{
+    const I8Plan pl = plan_i8(nq, nt, batch, sm_count);
+    return pl.splits > 1 ? (size_t)pl.splits * batch * nq * 2 * sizeof(unsigned long long) : 0;
+}
+
+size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare)
+{
+    size_t b = 256 + i8_partials_bytes(nq, nt, batch, sm_count);
+    b = (b + 1023) & ~(size_t)1023;
+    if (with_prepare) b += (prepared_bytes(nq) + prepared_bytes(nt)) * batch;
+    return b;
+}
+
+int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
+                            unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
+                            int sm_count, cudaStream_t stream)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        HM_CUDA_CHECK(cudaFuncSetAttribute(hm_i8_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        attr_set = true;
+    }
+    const I8Plan pl = plan_i8(nq, nt, batch, sm_count);
+    if ((long long)pl.ntiles * kBlockN > (1ll << 32)) {
+        set_error("train set too large for 32-bit trainIdx");
+        return HM_ERR_UNSUPPORTED;
+    }
+    const size_t need = 256 + i8_partials_bytes(nq, nt, batch, sm_count);
+    if (!ws || ws_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return HM_ERR_WORKSPACE;
+    }
+    I8Params P{};
+    P.qprep = static_cast<const uint8_t*>(qprep);
+    P.tprep = static_cast<const uint8_t*>(tprep);
+    P.nq = nq; P.nt = nt;
+    P.q_padded = padded_rows(nq);
+    P.t_padded = padded_rows(nt);
+    P.tiles_per_split = pl.tiles_per_split;
+    P.ntiles = pl.ntiles;
+    P.train_base = train_base;
+    P.error_flag = static_cast<int*>(ws);
+    const long long rows = nq * batch;
+    unsigned long long* partials = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + 256);
+    if (pl.splits > 1) {
+        P.out = partials;
+        P.out_split_stride = rows * 2;
+    } else {
+        P.out = out;
+        P.out_split_stride = 0;
+    }
+    if (pl.qblocks > 0x7FFFFFFFll || pl.splits > 65535 || batch > 65535) {
+        set_error("grid too large");
+        return HM_ERR_UNSUPPORTED;
+    }
+    dim3 grid((unsigned)pl.qblocks, (unsigned)pl.splits, (unsigned)batch);
+    hm_i8_knn2_kernel<<<grid, kThreads, kSmemBytes, stream>>>(P);
+    HM_CUDA_CHECK(cudaGetLastError());
+    if (pl.splits > 1) return launch_merge_top2(partials, pl.splits, rows, out, stream);
+    return HM_OK;
+}
+
+int launch_i8_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count,
+                   cudaStream_t stream)
+{
+    const size_t need = i8_workspace_bytes(p.nq, p.nt, p.batch, sm_count, true);
+    if (!ws || ws_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return HM_ERR_WORKSPACE;
+    }
+    const size_t head = i8_workspace_bytes(p.nq, p.nt, p.batch, sm_count, false);
+    uint8_t* qprep = static_cast<uint8_t*>(ws) + head;
+    uint8_t* tprep = qprep + prepared_bytes(p.nq) * p.batch;
+    int rc = launch_prepare(p.q, p.nq, p.q_stride, p.q_batch_stride, p.batch, qprep, stream);
+    if (rc != HM_OK) return rc;
+    rc = launch_prepare(p.t, p.nt, p.t_stride, p.t_batch_stride, p.batch, tprep, stream);
+    if (rc != HM_OK) return rc;
+    return launch_i8_knn2_prepared(qprep, p.nq, tprep, p.nt, p.batch, p.train_base, out, ws, head, sm_count, stream);
+}
+
+}  // namespace hm

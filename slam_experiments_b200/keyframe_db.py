@@ -1,0 +1,152 @@
+"""Keyframe-database matching with the train set sharded across the GPUs of one box.
+
+The reference keeps keyframes in ``Map._keyframes`` (`/root/reference/backend.py:31-37`) but
+never matches against them; the north-star workload maps onto cv2's
+train-collection API, ``bf.add([kf0, kf1, ...]); bf.knnMatch(query, k=2)``, whose result is the
+global stable top-k over the row concatenation reported as ``(imgIdx, trainIdx)``
+(SURVEY.md E5).  Here each rank (one process per GPU) keeps a contiguous range of keyframes
+resident, computes its local top-2 with global row ids, and the per-shard candidates are
+merged after ONE exchange step: an all-gather of ``Nq x 2`` packed 64-bit keys (32 KB per
+rank for 2000 queries) over NCCL / NVLink, followed by ``hm_merge_top2``.  Unsigned min over
+``(dist << 32 | global_row)`` is cv2's order because a lower global row is a lower
+``(imgIdx, trainIdx)``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .feature_matchers import MatcherError, _build_dmatches
+
+
+def shard_ranges(sizes: Sequence[int], world_size: int) -> List[Tuple[int, int, int, int]]:
+    """Contiguous keyframe ranges balanced by row count.
+
+    Returns, per rank, ``(kf_lo, kf_hi, row_lo, row_hi)``; ranges tile the collection in
+    order, so a lower rank always holds lower global rows.
+    """
+    sizes = np.asarray(sizes, dtype=np.int64)
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    total = int(starts[-1])
+    nkf = len(sizes)
+    out = []
+    lo = 0
+    for r in range(world_size):
+        target = total * (r + 1) // world_size
+        hi = int(np.searchsorted(starts, target, side="left"))
+        hi = max(lo, min(hi, nkf))
+        if r == world_size - 1:
+            hi = nkf
+        out.append((lo, hi, int(starts[lo]), int(starts[hi])))
+        lo = hi
+    return out
+
+
+class NativeOps:
+    """Device operations of the sharded path: the C ABI kernels + torch.distributed."""
+
+    def __init__(self, device=None, variant: str = "auto"):
+        self.device = nat.require_cuda(device)
+        self.variant = variant
+        nat.lib()
+
+    def upload(self, a: np.ndarray) -> torch.Tensor:
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8)).to(self.device)
+
+    def make_shard(self, train: torch.Tensor):
+        """Keep the shard resident; for the tensor-core variant also its prepared image."""
+        nt = train.shape[0]
+        use_i8 = self.variant == "i8" or (self.variant == "auto" and nt >= 65536)
+        prepared = nat.prepare(train) if (use_i8 and nt > 0) else None
+        return {"bits": train, "prepared": prepared, "nt": nt}
+
+    def local_knn2(self, query: torch.Tensor, shard, train_base: int) -> torch.Tensor:
+        if shard["prepared"] is not None and query.shape[0] > 0:
+            qprep = nat.prepare(query)
+            return nat.knn2_keys_prepared(qprep, query.shape[0], shard["prepared"], shard["nt"], train_base)
+        return nat.knn2_keys(query, shard["bits"], train_base=train_base, variant=self.variant)
+
+    def all_gather(self, keys: torch.Tensor, group) -> torch.Tensor:
+        import torch.distributed as dist
+        world = dist.get_world_size(group)
+        out = torch.empty((world,) + tuple(keys.shape), dtype=keys.dtype, device=keys.device)
+        dist.all_gather_into_tensor(out, keys.contiguous(), group=group)
+        return out
+
+    def merge(self, gathered: torch.Tensor) -> torch.Tensor:
+        return nat.merge_top2(gathered)
+
+    def to_host(self, keys: torch.Tensor) -> np.ndarray:
+        return keys.cpu().numpy()
+
+
+class ShardedKeyframeDatabase:
+    """Train collection sharded by contiguous keyframe ranges, one shard per rank.
+
+    ``sizes`` (rows per keyframe) is known to every rank; ``local_keyframes`` holds only this
+    rank's range ``shard_ranges(sizes, world)[rank]``.  With ``world_size == 1`` (or no process
+    group) it is the single-GPU resident database.
+    """
+
+    def __init__(self, sizes: Sequence[int], local_keyframes: Sequence[np.ndarray], *, rank: int = 0,
+                 world_size: int = 1, group=None, ops=None, device=None, variant: str = "auto"):
+        self.sizes = np.asarray(sizes, dtype=np.int64)
+        self.starts = np.concatenate([[0], np.cumsum(self.sizes)])
+        self.rank, self.world_size, self.group = rank, world_size, group
+        self.ops = ops if ops is not None else NativeOps(device, variant)
+        self.kf_lo, self.kf_hi, self.row_lo, self.row_hi = shard_ranges(self.sizes, world_size)[rank]
+        if len(local_keyframes) != self.kf_hi - self.kf_lo:
+            raise ValueError(f"rank {rank} owns keyframes [{self.kf_lo}, {self.kf_hi}) but got "
+                             f"{len(local_keyframes)} arrays")
+        for i, a in enumerate(local_keyframes):
+            a = np.asarray(a)
+            if a.dtype != np.uint8 or a.ndim != 2 or a.shape[1] != nat.DESC_BYTES:
+                raise MatcherError(f"keyframe {self.kf_lo + i}: expected uint8 [N, 32] descriptors")
+            if a.shape[0] != self.sizes[self.kf_lo + i]:
+                raise ValueError(f"keyframe {self.kf_lo + i}: {a.shape[0]} rows, sizes says "
+                                 f"{self.sizes[self.kf_lo + i]}")
+        cat = (np.concatenate([np.asarray(a) for a in local_keyframes], axis=0)
+               if len(local_keyframes) else np.empty((0, nat.DESC_BYTES), np.uint8))
+        self.shard = self.ops.make_shard(self.ops.upload(cat))
+
+    # ---- device-level API ---------------------------------------------------------------------
+    def knn2_keys_device(self, query_dev: torch.Tensor) -> torch.Tensor:
+        """Global top-2 keys ``[Nq, 2]`` (identical on every rank)."""
+        local = self.ops.local_knn2(query_dev, self.shard, self.row_lo)
+        if self.world_size == 1:
+            return local
+        gathered = self.ops.all_gather(local, self.group)
+        return self.ops.merge(gathered)
+
+    # ---- host-level API -----------------------------------------------------------------------
+    def knn_tensors(self, query: np.ndarray, k: int = 2):
+        """``(imgIdx, trainIdx, distance)`` each ``[Nq, k']``: cv2's collection result as arrays."""
+        if k not in (1, 2):
+            raise MatcherError("only k in {1, 2} is supported on the B200 path")
+        q = np.asarray(query)
+        if q.size == 0:
+            e = np.empty((0, 0), np.int32)
+            return e, e.copy(), e.copy()
+        if q.dtype != np.uint8 or q.ndim != 2 or q.shape[1] != nat.DESC_BYTES:
+            raise MatcherError("query: expected uint8 [N, 32] descriptors")
+        keys = self.ops.to_host(self.knn2_keys_device(self.ops.upload(q)))
+        gidx, dist, valid = nat.split_keys(keys)
+        kk = min(k, int(valid[0].sum()))
+        gidx, dist = gidx[:, :kk], dist[:, :kk]
+        img = (np.searchsorted(self.starts, gidx, side="right") - 1).astype(np.int32)
+        local = (gidx - self.starts[img]).astype(np.int32)
+        return img, local, dist
+
+    def knnMatch(self, queryDescriptors, k: int = 2) -> tuple:
+        """cv2 ``bf.knnMatch(query, k)`` over the whole (sharded) collection."""
+        img, local, dist = self.knn_tensors(queryDescriptors, k)
+        nq, kk = img.shape
+        if kk == 0:
+            return tuple(() for _ in range(nq))
+        qi = np.repeat(np.arange(nq, dtype=np.int32), kk)
+        flat = _build_dmatches(qi.tolist(), local.reshape(-1).tolist(),
+                               dist.reshape(-1).astype(np.float32).tolist(), img.reshape(-1).tolist())
+        return tuple(tuple(flat[i * kk:(i + 1) * kk]) for i in range(nq))

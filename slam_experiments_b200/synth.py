@@ -1,0 +1,71 @@
+"""Seeded synthetic descriptor workloads, shared by tests and bench.py.
+
+Distributions: (U) i.i.d. uniform bytes -- top-1 distances ~80-105 and ~20% of rows with a
+top1 == top2 tie, which stresses tie-breaking; (M) "matchable": 60% of the queries are a train
+row with each bit flipped w.p. 0.1, the rest uniform -- makes the ratio test and the mutual
+check non-trivial (real ORB bit density is 0.54).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+DESC_BYTES = 32
+
+
+def uniform(n: int, seed: int) -> np.ndarray:
+    return np.random.default_rng(seed).integers(0, 256, (n, DESC_BYTES), dtype=np.uint8)
+
+
+def matchable_queries(train: np.ndarray, nq: int, seed: int, flip_p: float = 0.1, frac: float = 0.6) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    nt = train.shape[0]
+    src = rng.integers(0, nt, nq)
+    q = train[src].copy()
+    noisy = rng.random(nq) < frac
+    k = int(noisy.sum())
+    if k:
+        flips = np.packbits(rng.random((k, 256)) < flip_p, axis=1)
+        q[noisy] ^= flips
+    if nq - k:
+        q[~noisy] = rng.integers(0, 256, (nq - k, DESC_BYTES), dtype=np.uint8)
+    return q
+
+
+def sweep(n: int, dist: str = "U"):
+    """C3: N x N, seed 1000 + log2(N)."""
+    seed = 1000 + int(np.log2(max(n, 1)))
+    t = uniform(n, seed)
+    q = uniform(n, seed + 100) if dist == "U" else matchable_queries(t, n, seed + 100)
+    return q, t
+
+
+def keyframe_database(n_keyframes: int = 4096, rows: int = 2000, nq: int = 2000, seed: int = 4096):
+    """C4: ``n_keyframes`` x ``rows`` train descriptors (one array [n_keyframes*rows, 32]) and a
+    matchable query whose true matches are scattered over the keyframes."""
+    rng = np.random.default_rng(seed)
+    train = rng.integers(0, 256, (n_keyframes * rows, DESC_BYTES), dtype=np.uint8)
+    q = matchable_queries(train, nq, seed + 1)
+    return q, train
+
+
+def frame_sequence(n_frames: int = 100, rows: int = 2000, seed: int = 752480, flip_p: float = 0.05) -> np.ndarray:
+    """C2-shaped: consecutive frames share most features (each frame = previous frame with a few
+    bits flipped, 30% of the rows replaced and the order shuffled).  [n_frames, rows, 32]."""
+    rng = np.random.default_rng(seed)
+    frames = np.empty((n_frames, rows, DESC_BYTES), dtype=np.uint8)
+    frames[0] = rng.integers(0, 256, (rows, DESC_BYTES), dtype=np.uint8)
+    for i in range(1, n_frames):
+        f = frames[i - 1].copy()
+        f ^= np.packbits(rng.random((rows, 256)) < flip_p, axis=1)
+        new = rng.random(rows) < 0.3
+        f[new] = rng.integers(0, 256, (int(new.sum()), DESC_BYTES), dtype=np.uint8)
+        frames[i] = f[rng.permutation(rows)]
+    return frames
+
+
+def local_window(n_frames: int = 32, rows: int = 10000, seed: int = 3200):
+    """C5: 32 train frames x 10,000 rows and one 10,000-row matchable query per frame."""
+    rng = np.random.default_rng(seed)
+    train = rng.integers(0, 256, (n_frames, rows, DESC_BYTES), dtype=np.uint8)
+    query = np.stack([matchable_queries(train[i], rows, seed + 1 + i) for i in range(n_frames)])
+    return query, train

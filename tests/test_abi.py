@@ -1,0 +1,62 @@
+"""The C-ABI library loads and exports every symbol include/hm_matcher.h declares.
+No compute calls here (no GPU in CI): compute entry points must fail loudly instead."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT
+from slam_experiments_b200 import _native as nat
+from slam_experiments_b200 import build as hm_build
+
+HEADER = os.path.join(ROOT, "include", "hm_matcher.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    hm_build.build()
+    return nat.lib()
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    return sorted(set(re.findall(r"HM_API\s+[\w\s\*]+?\b(hm_\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    assert declared_symbols() == sorted(nat.EXPORTS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    raw = ctypes.CDLL(nat.SO_PATH)
+    for name in declared_symbols():
+        assert hasattr(raw, name), f"{name} declared in hm_matcher.h but not exported"
+
+
+def test_version_and_sizing(lib):
+    assert lib.hm_version() == 1
+    assert lib.hm_prepared_bytes(0) == 0
+    assert lib.hm_prepared_bytes(1) == 256 * 256            # padded to whole 256-row tiles
+    assert lib.hm_prepared_bytes(257) == 512 * 256
+    for v in (0, 1, 2):
+        assert lib.hm_workspace_bytes(2000, 2000, 1, v) > 0
+    assert lib.hm_workspace_bytes(2000, 8192000, 1, 2) >= lib.hm_prepared_bytes(8192000)
+    assert lib.hm_select_variant(200, 200, 1) == nat.VARIANT_POPC
+    assert lib.hm_select_variant(16384, 16384, 1) == nat.VARIANT_I8
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_compute_fails_loudly_without_gpu(lib):
+    """No CPU fallback: every compute entry point reports HM_ERR_NO_DEVICE."""
+    buf = np.zeros((4, 32), dtype=np.uint8)
+    out = np.zeros((4, 2), dtype=np.uint64)
+    rc = lib.hm_knn2(buf.ctypes.data, 4, 32, buf.ctypes.data, 4, 32, 0, out.ctypes.data, 0, None, 0, None)
+    assert rc == -5 and b"no CUDA device" in lib.hm_last_error()
+    assert lib.hm_merge_top2(out.ctypes.data, 1, 2, out.ctypes.data, None) == -5
+    assert lib.hm_prepare(buf.ctypes.data, 4, 32, buf.ctypes.data, None) == -5
+    h = ctypes.c_void_p()
+    assert lib.hm_context_create(ctypes.byref(h)) == -5
+    assert lib.hm_device_sm_count() == -5

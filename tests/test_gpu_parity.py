@@ -1,0 +1,238 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bit-exact everywhere: this is integer work.  Every test runs BOTH kernel variants
+((a) POPC, (b) tcgen05 int8) unless the variant is irrelevant.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import slam_experiments_b200 as sx
+from slam_experiments_b200 import _native as nat
+from slam_experiments_b200 import synth
+from conftest import load_golden, pair_goldens, golden_files
+from oracle import hamming_oracle as ho
+from oracle import c_oracle as co
+
+pytestmark = pytest.mark.gpu
+cv2 = pytest.importorskip("cv2")
+VARIANTS = ("popc", "i8")
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def gpu_keys(q, t, variant, base=0):
+    return nat.knn2_keys(dev(q), dev(t), train_base=base, variant=variant).cpu().numpy().view(np.uint64)
+
+
+def _ids(paths):
+    return [os.path.basename(p)[:-4] for p in paths]
+
+
+def _rows(matches):
+    return [(m.queryIdx, m.trainIdx, m.imgIdx, int(m.distance)) for m in matches]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("path", pair_goldens(), ids=_ids(pair_goldens()))
+def test_golden_fixtures_through_dropin(path, variant):
+    """The reference's own outputs (tests/golden) reproduced by the drop-in classes."""
+    g = load_golden(path)
+    q, t = g["query"], g["train"]
+    m = sx.BruteForceFeatureMatcher(norm_type=cv2.NORM_HAMMING, variant=variant)
+    out = m.match(t, q)                                            # feature_matchers.py:36-39
+    assert isinstance(out, tuple) and _rows(out) == [tuple(r) for r in g["ref_match"].tolist()]
+    for th in (30, 64):                                            # feature_matchers.py:41-43
+        out = m.match(t, q, dist_threshold=float(th))
+        assert isinstance(out, list) and _rows(out) == [tuple(r) for r in g[f"ref_match_thr{th}"].tolist()]
+    for k in (1, 2):
+        rows = m.bf.knnMatch(q, t, k=k)
+        exp = g[f"knn{k}"]
+        assert len(rows) == exp.shape[0]
+        for r, e in zip(rows, exp):
+            assert _rows(r) == [tuple(x) for x in e.tolist() if x[0] >= 0]
+    cc = sx.BFMatcher(cv2.NORM_HAMMING, crossCheck=True, variant=variant)
+    assert _rows(cc.match(q, t)) == [tuple(r) for r in g["cross"].tolist()]
+    rows = cc.knnMatch(q, t, k=1)
+    assert [len(r) for r in rows] == [int(i in set(g["cross"][:, 0].tolist())) for i in range(q.shape[0])]
+    for r in (70, 75, 80):
+        pm = sx.BruteForceFeatureMatcher(cv2.NORM_HAMMING, ratio=r / 100.0, variant=variant)
+        assert _rows(pm.match(t, q)) == [tuple(x) for x in g[f"ratio{r}"].tolist()]
+        pm = sx.BruteForceFeatureMatcher(cv2.NORM_HAMMING, ratio=r / 100.0, cross_check=True, variant=variant)
+        assert _rows(pm.match(t, q)) == [tuple(x) for x in g[f"pipe{r}"].tolist()]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_collection_api_golden(variant):
+    g = load_golden(golden_files("collection_40.npz")[0])
+    starts = np.concatenate([[0], np.cumsum(g["sizes"])])
+    trains = [g["train_cat"][starts[i]:starts[i + 1]] for i in range(len(g["sizes"]))]
+    bf = sx.BFMatcher(cv2.NORM_HAMMING, variant=variant)
+    bf.add(trains)
+    rows = bf.knnMatch(g["query"], k=2)
+    assert [_rows(r) for r in rows] == [[tuple(x) for x in e.tolist()] for e in g["knn2"]]
+    assert _rows(bf.match(g["query"])) == [tuple(x) for x in g["match"].tolist()]
+    db = sx.ShardedKeyframeDatabase(g["sizes"], trains, variant=variant)
+    assert [_rows(r) for r in db.knnMatch(g["query"], 2)] == [[tuple(x) for x in e.tolist()] for e in g["knn2"]]
+
+
+SHAPES = [(1, 1), (1, 2), (2, 1), (3, 3), (31, 33), (32, 32), (33, 31), (127, 129), (128, 128), (129, 127),
+          (255, 257), (256, 256), (257, 255), (200, 200), (1000, 1000), (5, 3000), (3000, 5), (2000, 2000),
+          (640, 4096), (4100, 1030)]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+@pytest.mark.parametrize("nq,nt", SHAPES)
+def test_knn2_keys_vs_oracle_shapes(nq, nt, variant):
+    rng = np.random.default_rng(nq * 100003 + nt)
+    for hi in (256, 3):                        # uniform, and tie-heavy (every byte in {0,1,2})
+        q = rng.integers(0, hi, (nq, 32), dtype=np.uint8)
+        t = rng.integers(0, hi, (nt, 32), dtype=np.uint8)
+        assert np.array_equal(gpu_keys(q, t, variant), co.knn2_keys(q, t))
+    assert np.array_equal(gpu_keys(q, t, variant, base=12345), co.knn2_keys(q, t, train_base=12345))
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_adversarial_inputs(variant):
+    rng = np.random.default_rng(99)
+    nt = 1500
+    # all-equal: every pair ties -> indices 0 and 1 for every query
+    q = np.full((130, 32), 0x5A, np.uint8)
+    t = np.full((nt, 32), 0x5A, np.uint8)
+    k = gpu_keys(q, t, variant)
+    assert (k[:, 0] == 0).all() and (k[:, 1] == 1).all()
+    # monotonically improving distances: the top-2 update path fires on every train row
+    t = np.zeros((256, 32), np.uint8)
+    bits = np.zeros((256, 256), np.uint8)
+    for j in range(256):
+        bits[j, : 256 - j] = 1                 # row j has 256-j ones -> distance to zero query shrinks with j
+    t = np.packbits(bits, axis=1, bitorder="little")
+    q = np.zeros((64, 32), np.uint8)
+    assert np.array_equal(gpu_keys(q, t, variant), co.knn2_keys(q, t))
+    # extremes: distance 0 and 256
+    q = rng.integers(0, 256, (70, 32), dtype=np.uint8)
+    t = np.concatenate([~q[:35], q[35:]])
+    assert np.array_equal(gpu_keys(q, t, variant), co.knn2_keys(q, t))
+    # strided (non-contiguous) inputs, as cv2 accepts
+    wide = rng.integers(0, 256, (300, 64), dtype=np.uint8)
+    qs = torch.from_numpy(wide).cuda()[:, :32]
+    ts = torch.from_numpy(wide).cuda()[::2, 32:]
+    got = nat.knn2_keys(qs, ts, variant=variant).cpu().numpy().view(np.uint64)
+    assert np.array_equal(got, co.knn2_keys(wide[:, :32], wide[::2, 32:]))
+    bf = sx.BFMatcher(cv2.NORM_HAMMING, variant=variant)
+    ref = cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(wide[:, :32], wide[::2, 32:], k=2)
+    assert [_rows(r) for r in bf.knnMatch(wide[:, :32], wide[::2, 32:], k=2)] == [_rows(r) for r in ref]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_empty_and_short_train(variant):
+    bf = sx.BFMatcher(cv2.NORM_HAMMING, variant=variant)
+    q = np.arange(96, dtype=np.uint8).reshape(3, 32)
+    e = np.empty((0, 32), np.uint8)
+    assert bf.match(q, e) == () and bf.knnMatch(q, e, k=2) == ((), (), ())
+    rows = bf.knnMatch(q, q[:1], k=2)
+    assert [len(r) for r in rows] == [1, 1, 1]                                 # k = min(k, Nt)
+    assert sx.BruteForceFeatureMatcher(cv2.NORM_HAMMING, ratio=0.75, variant=variant).match(q[:1], q) == ()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_fused_pipeline_and_batched_vs_oracle(variant):
+    frames = synth.frame_sequence(6, 700, seed=5)
+    fd = torch.from_numpy(frames).cuda()
+    # overlapping windows: query = frame i+1, train = frame i (frontend.py:185-187), zero-copy
+    keys = nat.knn2_keys_batched(fd[1:], fd[:-1], variant=variant).cpu().numpy().view(np.uint64)
+    for i in range(5):
+        assert np.array_equal(keys[i], co.knn2_keys(frames[i + 1], frames[i]))
+    for ratio, cross, thr in ((0.8, True, None), (0.75, False, None), (None, True, None), (None, False, 40.0),
+                              (0.9, True, 64.5)):
+        oq, ot, od, cnt = nat.match_fused(fd[1:], fd[:-1], ratio=ratio, cross_check=cross, dist_threshold=thr,
+                                          variant=variant)
+        oq, ot, od, cnt = oq.cpu().numpy(), ot.cpu().numpy(), od.cpu().numpy(), cnt.cpu().numpy()
+        for i in range(5):
+            eq, et, ed = co.pipeline(frames[i + 1], frames[i], ratio=ratio, cross_check=cross)
+            if thr:
+                allq, allt, alld = ho.match(frames[i + 1], frames[i])
+                lim = max(2 * float(alld.min()), thr)
+                keep = ed.astype(np.float64) < lim
+                eq, et, ed = eq[keep], et[keep], ed[keep]
+            n = int(cnt[i])
+            assert n == len(eq)
+            assert np.array_equal(oq[i, :n], eq) and np.array_equal(ot[i, :n], et) and np.array_equal(od[i, :n], ed)
+
+
+def test_merge_top2_kernel_and_shard_split():
+    rng = np.random.default_rng(21)
+    q = rng.integers(0, 3, (333, 32), dtype=np.uint8)
+    t = rng.integers(0, 3, (5000, 32), dtype=np.uint8)
+    full = co.knn2_keys(q, t)
+    for cuts in ((0, 5000), (0, 1, 5000), (0, 1234, 1235, 4000, 5000), (0, 2500, 5000)):
+        parts = [nat.knn2_keys(dev(q), dev(t[a:b]), train_base=a, variant="popc" if i % 2 else "i8")
+                 for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:]))]
+        merged = nat.merge_top2(torch.stack(parts)).cpu().numpy().view(np.uint64)
+        assert np.array_equal(merged, full)
+
+
+def test_prepared_operands_resident_database():
+    q, t = synth.keyframe_database(16, 500, 300, seed=1)
+    qd, td = dev(q), dev(t)
+    tp = nat.prepare(td)
+    assert tp.numel() == nat.prepared_bytes(t.shape[0])
+    got = nat.knn2_keys_prepared(nat.prepare(qd), q.shape[0], tp, t.shape[0], train_base=77)
+    assert np.array_equal(got.cpu().numpy().view(np.uint64), co.knn2_keys(q, t, train_base=77))
+    # the prepared image really is the +/-1 expansion: dot == 256 - 2 * hamming
+    img = tp.cpu().numpy().view(np.int8)
+    assert set(np.unique(img[: 128 * 256]).tolist()) <= {-1, 1}
+
+
+def test_host_context_c_abi_only():
+    ctx = nat.HostContext()
+    rng = np.random.default_rng(2)
+    for nq, nt, v in ((200, 200, "auto"), (1000, 1300, "popc"), (1000, 1300, "i8"), (3, 1, "auto")):
+        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+        t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        assert np.array_equal(ctx.knn2_keys(q, t, v), co.knn2_keys(q, t))
+    ctx.close()
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_mid_size_vs_c_oracle(variant):
+    """8k x 8k uniform (C3 point) and a 2000 x 64k database slice (C4-shaped), bit-exact."""
+    q, t = synth.sweep(8192, "U")
+    assert np.array_equal(gpu_keys(q, t, variant), co.knn2_keys(q, t))
+    q, t = synth.keyframe_database(32, 2000, 2000, seed=4096)
+    assert np.array_equal(gpu_keys(q, t, variant), co.knn2_keys(q, t))
+
+
+def test_full_size_properties():
+    """BASELINE-size checks through size-independent properties (the oracle cannot run these).
+
+    64k x 64k sweep point: (1) both variants agree bit-for-bit; (2) planted exact duplicates are
+    found at distance 0 with the lowest index first; (3) permuting train rows permutes trainIdx
+    wherever the top-2 distances are tie-free; (4) a random sample of rows equals the oracle."""
+    n = 65536
+    q, t = synth.sweep(n, "M")
+    rng = np.random.default_rng(0)
+    planted = rng.choice(n, 64, replace=False)
+    t[planted] = q[planted]                    # query i == train i for the planted rows
+    dup = rng.choice(np.setdiff1d(np.arange(n), planted), 64, replace=False)
+    t[dup] = q[planted]                        # second copy elsewhere
+    qd, td = dev(q), dev(t)
+    k_i8 = nat.knn2_keys(qd, td, variant="i8").cpu().numpy().view(np.uint64)
+    k_pc = nat.knn2_keys(qd, td, variant="popc").cpu().numpy().view(np.uint64)
+    assert np.array_equal(k_i8, k_pc)
+    idx, dist, _ = nat.split_keys(k_i8)
+    assert (dist[planted] == 0).all()
+    assert np.array_equal(idx[planted, 0], np.minimum(planted, dup))
+    assert np.array_equal(idx[planted, 1], np.maximum(planted, dup))
+    sample = rng.choice(n, 256, replace=False)
+    assert np.array_equal(k_i8[sample], co.knn2_keys(q[sample], t))
+    perm = rng.permutation(n)
+    k_perm = nat.knn2_keys(qd, dev(t[perm]), variant="i8").cpu().numpy().view(np.uint64)
+    pidx, pdist, _ = nat.split_keys(k_perm)
+    assert np.array_equal(pdist, dist)         # distances are permutation invariant
+    tie_free = dist[:, 0] != dist[:, 1]
+    assert np.array_equal(perm[pidx[tie_free, 0]], idx[tie_free, 0])

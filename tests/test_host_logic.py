@@ -1,0 +1,113 @@
+"""Host-side logic of the drop-in classes that needs no GPU: cv2-compatible validation,
+empty-input short circuits, key decoding, ratio LUT, shard planning, loud failure without CUDA."""
+import numpy as np
+import pytest
+import torch
+
+import slam_experiments_b200 as sx
+from slam_experiments_b200 import _native as nat
+from slam_experiments_b200.feature_matchers import _build_dmatches
+from oracle import hamming_oracle as ho
+
+cv2 = pytest.importorskip("cv2")
+
+
+def test_constructor_signature_matches_reference():
+    m = sx.BruteForceFeatureMatcher(norm_type=cv2.NORM_HAMMING)       # slam.py:24
+    assert isinstance(m, sx.FeatureMatcher) and hasattr(m, "bf")
+    assert m.bf.empty() and m.bf.getTrainDescriptors() == ()
+    with pytest.raises(cv2.error):
+        sx.BruteForceFeatureMatcher(norm_type=cv2.NORM_L2)
+    with pytest.raises(TypeError):
+        sx.FeatureMatcher()                                             # abstract, like the reference ABC
+
+
+def test_empty_query_short_circuits_like_cv2():
+    m = sx.BruteForceFeatureMatcher(cv2.NORM_HAMMING)
+    t = np.zeros((5, 32), np.uint8)
+    assert m.match(t, np.array([])) == ()                               # Frame with no features
+    assert m.match(t, np.empty((0, 32), np.uint8)) == ()
+    assert m.bf.match(np.array([]), t) == ()
+    assert m.bf.knnMatch(np.array([]), t, k=2) == ()
+    assert m.bf.knnMatch(np.empty((0, 32), np.uint8), np.array([]), k=2) == ()
+
+
+def test_validation_raises_cv2_error():
+    bf = sx.BFMatcher(cv2.NORM_HAMMING)
+    q = np.zeros((3, 32), np.uint8)
+    for bad in (np.zeros((3, 32), np.float32), np.zeros((3, 32), np.int8), np.array([]),
+                np.zeros((3, 64), np.uint8), np.zeros((3, 16), np.uint8)):
+        with pytest.raises(cv2.error):
+            bf.match(q, bad)
+    with pytest.raises(cv2.error):
+        bf.match(q, q, mask=np.ones((3, 3), np.uint8))
+    with pytest.raises(cv2.error):
+        sx.BFMatcher(cv2.NORM_HAMMING, crossCheck=True).knnMatch(q, q, k=2)   # batch_distance.cpp:303
+    with pytest.raises(cv2.error):
+        bf.knnMatch(q, q, k=3)
+    with pytest.raises(TypeError):
+        bf.knnMatch(q, q)
+    with pytest.raises(cv2.error):
+        bf.add([np.zeros((1 << 18, 32), np.uint8)])                           # matchers.cpp:860
+    bf.add([np.zeros((4, 32), np.uint8), np.ones((2, 32), np.uint8)])
+    assert not bf.empty() and [a.shape for a in bf.getTrainDescriptors()] == [(4, 32), (2, 32)]
+    bf.clear()
+    assert bf.empty()
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_product_fails_loudly_without_gpu():
+    m = sx.BruteForceFeatureMatcher(cv2.NORM_HAMMING)
+    q = np.zeros((3, 32), np.uint8)
+    with pytest.raises(sx.NativeError, match="no CPU fallback"):
+        m.match(q, q)
+    with pytest.raises(sx.NativeError):
+        m.bf.knnMatch(q, q, k=2)
+
+
+def test_product_never_imports_the_oracle():
+    import os, re
+    from conftest import ROOT
+    pkg = os.path.join(ROOT, "slam_experiments_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "libhamming_oracle" not in src, f
+
+
+def test_ratio_lut_matches_oracle_and_float_compare():
+    for r in (0.6, 0.7, 0.75, 0.8, 0.9):
+        assert np.array_equal(nat.ratio_lut(r).astype(np.int32), ho.ratio_lut(r))
+
+
+def test_split_keys_roundtrip():
+    keys = np.array([[(7 << 32) | 5, nat.NO_MATCH], [(256 << 32) | 0xFFFFFFFE, (0 << 32) | 1]], dtype=np.uint64)
+    idx, dist, valid = nat.split_keys(keys.view(np.int64))
+    assert idx.tolist() == [[5, 0xFFFFFFFF], [0xFFFFFFFE, 1]]
+    assert dist[0, 0] == 7 and dist[1, 0] == 256 and dist[1, 1] == 0
+    assert valid.tolist() == [[True, False], [True, True]]
+
+
+def test_dmatch_fields_like_cv2():
+    ms = _build_dmatches([0, 1], [4, 3], [78.0, 12.0], 0)
+    assert [(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in ms] == [(0, 4, 0, 78.0), (1, 3, 0, 12.0)]
+    assert isinstance(ms[0], cv2.DMatch)
+    ms = _build_dmatches([0, 1], [4, 3], [78.0, 12.0], [2, 5])
+    assert [m.imgIdx for m in ms] == [2, 5]
+
+
+def test_shard_ranges_tile_the_collection():
+    rng = np.random.default_rng(3)
+    for world in (1, 2, 3, 4, 8):
+        for sizes in ([2000] * 4096, rng.integers(0, 50, 37).tolist(), [5], [0, 0, 7, 0], [1] * 3):
+            r = sx.shard_ranges(sizes, world)
+            assert len(r) == world and r[0][0] == 0 and r[-1][1] == len(sizes)
+            starts = np.concatenate([[0], np.cumsum(sizes)])
+            for a, b in zip(r[:-1], r[1:]):
+                assert a[1] == b[0] and a[3] == b[2]
+            for kf_lo, kf_hi, row_lo, row_hi in r:
+                assert kf_lo <= kf_hi and row_lo == starts[kf_lo] and row_hi == starts[kf_hi]
+    r = sx.shard_ranges([2000] * 4096, 8)
+    assert all(hi - lo == 512 for lo, hi, _, _ in r)
