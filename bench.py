@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the Hamming brute-force matching hot path on B200.
+
+Default workload (BASELINE.json configs[3], the one quoted at 1/2/4/8 GPUs): the
+keyframe-database query -- 2000 query descriptors against 4096 keyframes x 2000 train
+descriptors (8,192,000 rows), the train set sharded across the N GPUs of one box by contiguous
+keyframe ranges, per-shard top-2 candidates merged after one NCCL all-gather.  A "step" is one
+query batch against the whole database.  `value` is whole-job Gpairs/s with the database and the
+query already resident in HBM; `e2e` is the same metric through the reference-facing drop-in
+(`ShardedKeyframeDatabase.knnMatch`, the cv2 collection API `bf.add(...); bf.knnMatch(q, k=2)`)
+with the query in host memory and DMatch tuples out.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...
+
+Other workloads (--workload c2|c3|c5) are single-GPU lines used for DESIGN.md / profiles.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "hamming_pairs_per_sec"
+UNIT = "Gpairs/s"
+NQ = 2000
+KF_ROWS = 2000
+N_KEYFRAMES = 4096
+I8_OPS_PER_PAIR = 512           # 256 MAC on the +/-1 expansion
+POPC_PER_PAIR = 8
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_c4(n_keyframes=N_KEYFRAMES, rows=KF_ROWS, nq=NQ):
+    from slam_experiments_b200 import synth
+    return synth.keyframe_database(n_keyframes, rows, nq, seed=4096)
+
+
+# =====================================================================================================
+# reference arm: the reference's own CPU implementation of the path (cv2.BFMatcher, the engine
+# /root/reference/feature_matchers.py:34,39 calls), all host threads, bounded sample per step
+# =====================================================================================================
+def cv2_collection_step(query, keyframes):
+    import cv2
+    bf = cv2.BFMatcher(cv2.NORM_HAMMING)
+    bf.add(keyframes)
+    return bf.knnMatch(query, k=2)
+
+
+def calibrate_sample(query, train, target_s: float, rows=KF_ROWS, max_kf=N_KEYFRAMES):
+    """Number of keyframes whose cv2 collection query takes about `target_s` seconds."""
+    probe = 32
+    kfs = [train[i * rows:(i + 1) * rows] for i in range(probe)]
+    cv2_collection_step(query, kfs)
+    t0 = time.perf_counter()
+    cv2_collection_step(query, kfs)
+    dt = max(time.perf_counter() - t0, 1e-4)
+    n = int(probe * target_s / dt)
+    return max(probe, min(max_kf, n))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import cv2
+    from oracle import cv2_ref  # noqa: F401  (the reference class restated over cv2; checker-side code)
+    query, train = make_c4()
+    per_step = 3.0
+    n_kf = calibrate_sample(query, train, per_step)
+    kfs = [train[i * KF_ROWS:(i + 1) * KF_ROWS] for i in range(n_kf)]
+    for _ in range(args.warmup):
+        cv2_collection_step(query, kfs)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cv2_collection_step(query, kfs)
+    dt = time.perf_counter() - t0
+    pairs = float(NQ) * n_kf * KF_ROWS * args.steps
+    value = pairs / dt / 1e9
+    sample = f"{NQ} queries x {n_kf} of {N_KEYFRAMES} keyframes x {KF_ROWS} rows per step (cv2 collection API)"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": c4_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cv2.getNumThreads(), "kind": "reference",
+                         "sample": sample, "engine": f"cv2.BFMatcher {cv2.__version__}",
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def c4_config(n_gpus):
+    return {"workload": "c4_keyframe_database", "queries": NQ, "keyframes": N_KEYFRAMES, "rows_per_keyframe": KF_ROWS,
+            "train_rows": N_KEYFRAMES * KF_ROWS, "descriptor_bits": 256, "k": 2,
+            "sharding": f"train rows over {n_gpus} GPU(s), contiguous keyframe ranges",
+            "l2": "inputs larger than L2 (resident shard >= 262 MB per GPU)"}
+
+
+# =====================================================================================================
+# B200 arm
+# =====================================================================================================
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import slam_experiments_b200 as sx
+    from slam_experiments_b200 import _native as nat
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun --nproc-per-node N for --gpus N > 1")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    peaks, peak_src = measured_peaks()
+    query, train = make_c4()
+    sizes = [KF_ROWS] * N_KEYFRAMES
+    kf_lo, kf_hi, row_lo, row_hi = sx.shard_ranges(sizes, world)[rank]
+    local_kfs = [train[i * KF_ROWS:(i + 1) * KF_ROWS] for i in range(kf_lo, kf_hi)]
+    db = sx.ShardedKeyframeDatabase(sizes, local_kfs, rank=rank, world_size=world,
+                                    group=None if world == 1 else dist.group.WORLD, device=dev, variant=args.variant)
+    del local_kfs
+    q_dev = torch.from_numpy(query).to(dev)
+    nt_local = row_hi - row_lo
+    variant_used = "i8" if db.shard["prepared"] is not None else args.variant
+
+    # ---- correctness of what is timed (outside the timed region): sample of rows vs the oracle ----
+    verified = None
+    if not args.no_verify:
+        from oracle import c_oracle
+        keys = db.knn2_keys_device(q_dev).cpu().numpy().view(np.uint64)
+        if rank == 0:
+            sample = np.linspace(0, NQ - 1, 48).astype(np.int64)
+            verified = bool(np.array_equal(keys[sample], c_oracle.knn2_keys(query[sample], train)))
+            if not verified:
+                raise SystemExit("bench: GPU result differs from the oracle")
+
+    def step():
+        return db.knn2_keys_device(q_dev)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+
+    # ---- timed region: K steps, inputs resident ---------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        nat.profile_events(*kern_ev[i])
+        step()
+    e1.record()
+    barrier()
+    nat.profile_events(None, None)
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
+    t = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, kern_ms_max = float(t[0]), float(t[1])
+    ms_per_step = ms_total / args.steps
+    total_pairs = float(NQ) * N_KEYFRAMES * KF_ROWS
+    value = total_pairs / (ms_per_step * 1e-3) / 1e9
+
+    # ---- e2e: through the drop-in, host buffers in, DMatch tuples out --------------------------------
+    def e2e_loop(fn, steps):
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt[0]) / steps
+
+    e2e_s = e2e_loop(lambda: db.knnMatch(query, 2), args.steps)
+    e2e_arr_s = e2e_loop(lambda: db.knn_tensors(query, 2), args.steps)
+    e2e_value = total_pairs / e2e_s / 1e9
+
+    # ---- roofline of the dominant kernel (this rank's shard), from the live CUDA-event timing -----------
+    local_pairs = float(NQ) * nt_local
+    if variant_used == "i8":
+        achieved = local_pairs * I8_OPS_PER_PAIR / (kern_ms_max * 1e-3) / 1e12
+        peak = 2.0 * peaks["bf16_tflops_sustained"]
+        roofline = {"bound": "tensor", "kernel": "hm_i8_knn2_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "note": f"int8 ops (512/pair); peak = 2 x bf16_tflops_sustained of {peak_src} "
+                            "(kind::i8 issues at twice the bf16 rate)",
+                    "kernel_ms": kern_ms_max, "pairs_per_launch": local_pairs,
+                    "hbm_gbs": (nt_local * 256 + NQ * 256) / (kern_ms_max * 1e-3) / 1e9}
+    else:
+        sm = nat.sm_count()
+        achieved = local_pairs * POPC_PER_PAIR / (kern_ms_max * 1e-3) / 1e12
+        peak = sm * 16 * peaks["sm_max_mhz"] * 1e6 / 1e12
+        roofline = {"bound": "tensor", "kernel": "hm_popc_knn2_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "note": "POPC issue roofline (not tensor): T-popc/s, 8 per pair; peak = SMs x 16/clk x sm_max_mhz",
+                    "kernel_ms": kern_ms_max, "pairs_per_launch": local_pairs}
+    traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_file):
+        try:
+            with open(traffic_file) as f:
+                roofline["traffic"] = json.load(f).get(f"c4_n{world}_{variant_used}")
+        except Exception:
+            pass
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "u8", "data": "synthetic", "config": dict(c4_config(world), variant=variant_used,
+                                                         db_format="train shard resident as +/-1 int8 (expanded once at add())"),
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * 32, "d2h_bytes_per_step": NQ * 16,
+                "ms_per_step": e2e_s * 1e3, "api": "ShardedKeyframeDatabase.knnMatch(query_numpy, 2) -> DMatch tuples",
+                "arrays_out_ms_per_step": e2e_arr_s * 1e3},
+        "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
+        "roofline": roofline,
+        "verified_vs_oracle": verified,
+    }
+
+    # ---- cpu baseline beside it (rank 0, N=1 only): cv2 on the host cores, bounded sample ----------------
+    if world == 1 and not args.no_cpu_baseline:
+        import cv2
+        n_kf = calibrate_sample(query, train, 12.0)
+        kfs = [train[i * KF_ROWS:(i + 1) * KF_ROWS] for i in range(n_kf)]
+        t0 = time.perf_counter()
+        cv2_collection_step(query, kfs)
+        dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {
+            "value": float(NQ) * n_kf * KF_ROWS / dt / 1e9, "unit": UNIT, "cores": cv2.getNumThreads(),
+            "kind": "reference",
+            "sample": f"{NQ} queries x {n_kf} of {N_KEYFRAMES} keyframes x {KF_ROWS} rows, one cv2 collection knnMatch(k=2)",
+            "engine": f"cv2.BFMatcher {cv2.__version__}", "host_cpus": os.cpu_count(), "seconds": dt}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "popc", "i8"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
+    ap.add_argument("--n", type=int, default=65536, help="c3: N x N")
+    ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload != "c4":
+        from tools import bench_extra
+        return bench_extra.run(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

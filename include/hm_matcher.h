@@ -84,6 +84,13 @@ HM_API int hm_select_variant(int64_t nq, int64_t nt, int batch);
 /* scratch bytes hm_knn2* / hm_match_fused* need for this shape (variant may be AUTO) */
 HM_API size_t hm_workspace_bytes(int64_t nq, int64_t nt, int batch, int variant);
 
+/* ---- measurement hook ---------------------------------------------------------------- */
+/* When both are non-NULL (cudaEvent_t as void*), every later k-NN call of this thread records
+ * `start` immediately before and `stop` immediately after the launch of its dominant kernel
+ * (hm_popc_knn2_kernel or hm_i8_knn2_kernel) on the call's stream, so bench.py can time that
+ * kernel alone with CUDA events.  Pass NULLs to switch it off.  Not part of the data path. */
+HM_API void hm_profile_events(void* start_event, void* stop_event);
+
 /* ---- k-NN core: replaces cv2.BFMatcher.knnMatch(query, train, k=2) and, through key[0],
  *      cv2.BFMatcher.match(query, train) = /root/reference/feature_matchers.py:39 -------- */
 /* out_keys[nq][2]; train_base is added to every trainIdx (global row id of a shard's first row) */

@@ -29,7 +29,7 @@ PREPARED_ROW_BYTES = 256
 
 # every symbol include/hm_matcher.h declares (tests check the library exports all of them)
 EXPORTS = (
-    "hm_version", "hm_last_error", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
+    "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
     "hm_knn2", "hm_knn2_batched", "hm_prepared_bytes", "hm_prepare", "hm_knn2_prepared",
     "hm_merge_top2", "hm_filter_matches", "hm_match_fused",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host",
@@ -50,6 +50,8 @@ def _declare(L):
     L.hm_version.restype = ci
     L.hm_last_error.restype = c.c_char_p
     L.hm_device_sm_count.restype = ci
+    L.hm_profile_events.restype = None
+    L.hm_profile_events.argtypes = [vp, vp]
     L.hm_select_variant.restype = ci
     L.hm_select_variant.argtypes = [i64, i64, ci]
     L.hm_workspace_bytes.restype = sz
@@ -287,6 +289,18 @@ def match_fused(query: torch.Tensor, train: torch.Tensor, ratio: Optional[float]
                                _stream_ptr(dev)), "hm_match_fused")
     del lut
     return (oq, ot, od, cnt, keys) if want_keys else (oq, ot, od, cnt)
+
+
+def profile_events(start: Optional[torch.cuda.Event], stop: Optional[torch.cuda.Event]) -> None:
+    """``hm_profile_events``: record ``start``/``stop`` around the dominant kernel of later calls
+    made from this thread (events must have been created with ``enable_timing=True``)."""
+    if start is None or stop is None:
+        lib().hm_profile_events(None, None)
+        return
+    for e in (start, stop):          # torch creates the cudaEvent lazily on first record
+        if not e.cuda_event:
+            e.record()
+    lib().hm_profile_events(start.cuda_event, stop.cuda_event)
 
 
 def sm_count() -> int:

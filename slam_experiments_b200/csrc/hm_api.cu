@@ -22,6 +22,14 @@ void set_error(const char* fmt, ...)
     va_end(ap);
 }
 
+static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+
+void profile_mark(bool start, cudaStream_t stream)
+{
+    cudaEvent_t e = start ? g_prof_start : g_prof_stop;
+    if (g_prof_start && g_prof_stop) cudaEventRecord(e, stream);
+}
+
 int device_info(DeviceInfo* out)
 {
     static std::mutex mu;
@@ -158,6 +166,12 @@ extern "C" {
 HM_API int hm_version(void) { return HM_ABI_VERSION; }
 
 HM_API const char* hm_last_error(void) { return g_error; }
+
+HM_API void hm_profile_events(void* start_event, void* stop_event)
+{
+    g_prof_start = static_cast<cudaEvent_t>(start_event);
+    g_prof_stop = static_cast<cudaEvent_t>(stop_event);
+}
 
 HM_API int hm_device_sm_count(void)
 {

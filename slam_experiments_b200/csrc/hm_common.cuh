@@ -43,6 +43,9 @@ struct DeviceInfo {
 // cached per device; returns an hm_status
 int device_info(DeviceInfo* out);
 
+// optional event pair recorded around the dominant kernel (hm_profile_events)
+void profile_mark(bool start, cudaStream_t stream);
+
 inline __host__ __device__ long long ceil_div(long long a, long long b) { return (a + b - 1) / b; }
 
 // insert `key` into the ascending pair (k1, k2)

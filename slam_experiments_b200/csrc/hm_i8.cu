@@ -412,7 +412,9 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
         return HM_ERR_UNSUPPORTED;
     }
     dim3 grid((unsigned)pl.qblocks, (unsigned)pl.splits, (unsigned)batch);
+    profile_mark(true, stream);
     hm_i8_knn2_kernel<<<grid, kThreads, kSmemBytes, stream>>>(P);
+    profile_mark(false, stream);
     HM_CUDA_CHECK(cudaGetLastError());
     if (pl.splits > 1) return launch_merge_top2(partials, pl.splits, rows, out, stream);
     return HM_OK;

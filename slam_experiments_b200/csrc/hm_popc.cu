@@ -222,10 +222,12 @@ int launch_popc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, siz
         return HM_ERR_UNSUPPORTED;
     }
     dim3 grid((unsigned)qtiles, (unsigned)splits, (unsigned)p.batch);
+    profile_mark(true, stream);
     if (qpt == 2)
         hm_popc_knn2_kernel<2><<<grid, kThreads, 0, stream>>>(P);
     else
         hm_popc_knn2_kernel<1><<<grid, kThreads, 0, stream>>>(P);
+    profile_mark(false, stream);
     HM_CUDA_CHECK(cudaGetLastError());
     if (splits > 1) return launch_merge_top2(P.out, splits, rows, out, stream);
     return HM_OK;

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
-from .feature_matchers import MatcherError, _build_dmatches
+from .feature_matchers import MatcherError, _Staging, _build_dmatches
 
 
 def shard_ranges(sizes: Sequence[int], world_size: int) -> List[Tuple[int, int, int, int]]:
@@ -51,9 +51,15 @@ class NativeOps:
     def __init__(self, device=None, variant: str = "auto"):
         self.device = nat.require_cuda(device)
         self.variant = variant
+        self._staging = _Staging()
         nat.lib()
 
     def upload(self, a: np.ndarray) -> torch.Tensor:
+        """Host -> device through a reused pinned buffer (queries); big one-off uploads go direct."""
+        a = np.asarray(a)
+        if a.nbytes <= (8 << 20):
+            with torch.cuda.device(self.device):
+                return self._staging.to_device("q", a, self.device)
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8)).to(self.device)
 
     def make_shard(self, train: torch.Tensor):
@@ -80,7 +86,8 @@ class NativeOps:
         return nat.merge_top2(gathered)
 
     def to_host(self, keys: torch.Tensor) -> np.ndarray:
-        return keys.cpu().numpy()
+        with torch.cuda.device(self.device):
+            return self._staging.to_host("keys", keys)
 
 
 class ShardedKeyframeDatabase:
