@@ -9,6 +9,14 @@
 // tcgen05.ld (thread = query row, registers = train columns) and keep the running
 // top-2 in registers, so the 128x256 distance tile never leaves the SM.
 //
+// The +/-1 operands are 8x larger than the packed bits, so a single CTA streaming 64 KB of B
+// per 1024-cycle tile is bound by L2->SM bandwidth (ncu: 5.7 TB/s of xbar2l1tex reads at 31 %
+// tensor-pipe activity, profiles/r01a_*).  CTAs are therefore launched as thread-block clusters
+// of 2 or 4 neighbouring query blocks that share every train tile: each CTA fetches 1/CS of the
+// tile and multicasts it into the shared memory of all CS CTAs (cp.async.bulk ...
+// .multicast::cluster), and a stage is released by the multicast tcgen05.commit of all CS MMA
+// issuers.
+//
 // Replaces the same cv::batchDistance loop as hm_popc.cu
 // (/root/reference/feature_matchers.py:39 -> cv2.BFMatcher).
 //
@@ -16,6 +24,8 @@
 // blocks of 128 rows x 128 bytes (one K slab) laid out exactly as the UMMA K-major
 // SWIZZLE_128B shared-memory image, so a block is one contiguous 16 KB bulk copy
 // (cp.async.bulk / UBLKCP) with no tensor map.
+#include <stdlib.h>
+
 #include "hm_common.cuh"
 #include "hm_tcgen05.cuh"
 
@@ -33,8 +43,10 @@ constexpr int kStages = 2;
 constexpr int kABytes = 2 * kSlabBytes;      // 32 KB
 constexpr int kBStageBytes = 4 * kSlabBytes; // 64 KB
 constexpr int kTmemCols = 512;
-constexpr int kThreads = 192;                // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
-constexpr int kSmemBytes = 1024 + kABytes + kStages * kBStageBytes + 256;
+constexpr int kEpilogueWarps = 8;            // two per TMEM lane quarter: each takes one 128-column half
+constexpr int kThreads = 64 + 32 * kEpilogueWarps;   // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int kMergeBytes = kBlockM * 16;    // upper-half partial top-2 (two 64-bit keys per row)
+constexpr int kSmemBytes = 1024 + kABytes + kStages * kBStageBytes + 256 + kMergeBytes;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
 static_assert(kPadRows % kBlockN == 0 && kPadRows % kBlockM == 0, "prepared padding must cover whole tiles");
@@ -95,6 +107,7 @@ struct I8Params {
     unsigned long long* out;         // [split][batch][nq][2]
     long long out_split_stride;      // keys
     int* error_flag;
+    long long q_blocks_valid;        // 128-row blocks present in qprep (CTAs beyond it are cluster padding)
 };
 
 struct Top2 {
@@ -127,28 +140,37 @@ __device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32])
                  : "memory");
 }
 
-// 32 consecutive train columns of one query row.  Fast path: one 3-input-max tree per 8
-// columns against the running second best; the exact (value, index) insertion only runs for
-// groups that can change the top-2.  Strict '>' keeps the lowest train index on ties because
-// columns are visited in ascending order.
+// 32 consecutive train columns of one query row.  Fast path: 3-input-max trees give the maximum
+// of each group of 8 columns and of the whole chunk; one compare + branch per chunk against the
+// running second best decides whether anything can change the top-2.  Only then are the groups
+// revisited, and the exact (value, index) insertion runs for the groups that still qualify.
+// Strict '>' keeps the lowest train index on ties because columns are visited in ascending order.
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], unsigned colbase, unsigned limit, Top2& s)
 {
+    int gm[4];
 #pragma unroll
-    for (int g = 0; g < 32; g += 8) {
-        const int m = __vimax3_s32(__vimax3_s32((int)r[g], (int)r[g + 1], (int)r[g + 2]),
-                                   __vimax3_s32((int)r[g + 3], (int)r[g + 4], (int)r[g + 5]),
-                                   max((int)r[g + 6], (int)r[g + 7]));
-        if (m > s.v2) {
+    for (int g = 0; g < 4; ++g) {
+        const int o = g * 8;
+        gm[g] = __vimax3_s32(__vimax3_s32((int)r[o], (int)r[o + 1], (int)r[o + 2]),
+                             __vimax3_s32((int)r[o + 3], (int)r[o + 4], (int)r[o + 5]),
+                             max((int)r[o + 6], (int)r[o + 7]));
+    }
+    const int m = __vimax3_s32(gm[0], gm[1], max(gm[2], gm[3]));
+    if (m > s.v2) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const int x = (int)r[g + e];
-                const unsigned idx = colbase + g + e;
-                if (x > s.v2 && idx < limit) {
-                    if (x > s.v1) {
-                        s.v2 = s.v1; s.i2 = s.i1;
-                        s.v1 = x;    s.i1 = idx;
-                    } else {
-                        s.v2 = x;    s.i2 = idx;
+        for (int g = 0; g < 4; ++g) {
+            if (gm[g] > s.v2) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int x = (int)r[g * 8 + e];
+                    const unsigned idx = colbase + g * 8 + e;
+                    if (x > s.v2 && idx < limit) {
+                        if (x > s.v1) {
+                            s.v2 = s.v1; s.i2 = s.i1;
+                            s.v1 = x;    s.i1 = idx;
+                        } else {
+                            s.v2 = x;    s.i2 = idx;
+                        }
                     }
                 }
             }
@@ -170,12 +192,18 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
     uint64_t* tmem_full_bar = bars + 2 * kStages + 1;   // [2] accumulator complete
     uint64_t* tmem_empty_bar = bars + 2 * kStages + 3;  // [2] accumulator drained by the epilogue
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
+    ulonglong2* merge_slot = reinterpret_cast<ulonglong2*>(smem + kABytes + kStages * kBStageBytes + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int qb = blockIdx.x;
     const int split = blockIdx.y;
     const int b = blockIdx.z;
+
+    const uint32_t cs = ptx::cluster_nctarank();            // 1, 2 or 4 CTAs sharing the B tiles
+    const uint32_t crank = ptx::cluster_ctarank();
+    const uint16_t cmask = (uint16_t)((1u << cs) - 1);
+    const bool has_a = qb < P.q_blocks_valid;
 
     const int tile_begin = split * P.tiles_per_split;
     const int tile_end = min(tile_begin + P.tiles_per_split, P.ntiles);
@@ -184,12 +212,12 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], cs);           // one multicast commit per CTA of the cluster
         }
         ptx::mbar_init(a_full_bar, 1);
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], 4);       // one arrival per epilogue warp
+            ptx::mbar_init(&tmem_empty_bar[i], kEpilogueWarps);   // one arrival per epilogue warp
         }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -198,7 +226,8 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
         ptx::tmem_relinquish();
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (cs > 1) ptx::cluster_sync();   // peers' barriers are initialised before any multicast lands
+    else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
@@ -206,8 +235,10 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
         // ===== producer: bulk async copies global -> shared =====
         if (lane == 0) {
             const uint8_t* qsrc = P.qprep + ((long long)b * P.q_padded + (long long)qb * kBlockM) * HM_PREPARED_ROW_BYTES;
-            ptx::mbar_arrive_expect_tx(a_full_bar, kABytes);
-            ptx::bulk_g2s(smem_a, qsrc, kABytes, a_full_bar);          // [slab0 | slab1] of one row block
+            if (has_a) {
+                ptx::mbar_arrive_expect_tx(a_full_bar, kABytes);
+                ptx::bulk_g2s(smem_a, qsrc, kABytes, a_full_bar);      // [slab0 | slab1] of one row block
+            }
             const uint8_t* tsrc = P.tprep + (long long)b * P.t_padded * HM_PREPARED_ROW_BYTES;
             for (int i = 0; i < my_tiles; ++i) {
                 const int stage = i % kStages;
@@ -216,11 +247,15 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
                 ptx::mbar_arrive_expect_tx(&full_bar[stage], kBStageBytes);
                 uint8_t* dst = smem_b + stage * kBStageBytes;
                 const uint8_t* src = tsrc + (long long)(tile_begin + i) * 2 * kRowBlockBytes;
-                // stage image: [slab0: rows 0-127 | rows 128-255][slab1: rows 0-127 | rows 128-255]
-                ptx::bulk_g2s(dst,                  src,                               kSlabBytes, &full_bar[stage]);
-                ptx::bulk_g2s(dst + kSlabBytes,     src + kRowBlockBytes,              kSlabBytes, &full_bar[stage]);
-                ptx::bulk_g2s(dst + 2 * kSlabBytes, src + kSlabBytes,                  kSlabBytes, &full_bar[stage]);
-                ptx::bulk_g2s(dst + 3 * kSlabBytes, src + kRowBlockBytes + kSlabBytes, kSlabBytes, &full_bar[stage]);
+                // stage image: [slab0: rows 0-127 | rows 128-255][slab1: rows 0-127 | rows 128-255];
+                // piece p (16 KB) = row block (p & 1), slab (p >> 1).  This CTA fetches 4/cs pieces and
+                // multicasts them; the other pieces arrive from its cluster peers.
+                const int per = 4 / (int)cs;
+                for (int p = (int)crank * per; p < ((int)crank + 1) * per; ++p) {
+                    const uint8_t* psrc = src + (p & 1) * kRowBlockBytes + (p >> 1) * kSlabBytes;
+                    if (cs > 1) ptx::bulk_g2s_multicast(dst + p * kSlabBytes, psrc, kSlabBytes, &full_bar[stage], cmask);
+                    else        ptx::bulk_g2s(dst + p * kSlabBytes, psrc, kSlabBytes, &full_bar[stage]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -228,7 +263,7 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
         constexpr uint32_t idesc = ptx::make_i8_idesc(kBlockM, kBlockN);
         const uint32_t a_addr = ptx::smem_u32(smem_a);
         const uint32_t b_addr = ptx::smem_u32(smem_b);
-        bounded_wait(a_full_bar, 0, P.error_flag);
+        if (has_a) bounded_wait(a_full_bar, 0, P.error_flag);
         for (int i = 0; i < my_tiles; ++i) {
             const int stage = i % kStages;
             const uint32_t use = i / kStages;
@@ -248,54 +283,68 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
                         ptx::mma_i8_ss(tmem_base + acc * kBlockN, da, db, idesc, (s | k) != 0);
                     }
                 }
-                ptx::tc_commit(&empty_bar[stage]);        // smem stage reusable once these MMAs retire
+                // smem stage reusable (by every producer of the cluster) once these MMAs retire
+                if (cs > 1) ptx::tc_commit_multicast(&empty_bar[stage], cmask);
+                else        ptx::tc_commit(&empty_bar[stage]);
                 ptx::tc_commit(&tmem_full_bar[acc]);      // accumulator ready for the epilogue
             }
             __syncwarp();
         }
     } else {
         // ===== epilogue: TMEM -> registers, running top-2 per query row =====
+        // Warps 2..5 scan columns [0,128) of every tile, warps 6..9 columns [128,256) of the same rows,
+        // so each SM sub-partition has two epilogue warps to overlap TMEM loads with the scan.
         const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
-        const long long row = (long long)qb * kBlockM + quarter * 32 + lane;
+        const int half = (warp - 2) >> 2;                 // which 128-column half of the tile
+        const int row_in_block = quarter * 32 + lane;
+        const long long row = (long long)qb * kBlockM + row_in_block;
         Top2 s;
         s.v1 = s.v2 = INT_MIN;
         s.i1 = s.i2 = 0;
         const long long first_row = (long long)tile_begin * kBlockN;
         const unsigned limit = (unsigned)min((long long)my_tiles * kBlockN, P.nt - first_row);
+        constexpr int kChunks = kBlockN / 32 / 2;         // chunks of 32 columns per warp per tile
         for (int i = 0; i < my_tiles; ++i) {
             const int acc = i & 1;
             const uint32_t acc_use = i >> 1;
             bounded_wait(&tmem_full_bar[acc], acc_use & 1, P.error_flag);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN;
-            const unsigned colbase = (unsigned)i * kBlockN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * (kBlockN / 2);
+            const unsigned colbase = (unsigned)i * kBlockN + half * (kBlockN / 2);
             uint32_t ra[32], rb[32];
             ptx::tmem_ld_32x32(taddr, ra);
-#pragma unroll
-            for (int c = 0; c < kBlockN / 32; c += 2) {
+#pragma unroll 1   // keep the loop body (two chunks) resident in the instruction cache
+            for (int c = 0; c < kChunks; c += 2) {
                 tmem_ld_fence(ra);
                 ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
                 scan_chunk(ra, colbase + c * 32, limit, s);
                 tmem_ld_fence(rb);
-                if (c + 2 < kBlockN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
+                if (c + 2 < kChunks) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
                 scan_chunk(rb, colbase + (c + 1) * 32, limit, s);
             }
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
         }
-        if (row < P.nq) {
-            const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
-            ulonglong2 k;
-            k.x = s.v1 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v1) >> 1) << 32) | (gbase + s.i1);
-            k.y = s.v2 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v2) >> 1) << 32) | (gbase + s.i2);
+        // widen to 64-bit global keys; the upper-half warps hand theirs over through shared memory
+        const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
+        ulonglong2 k;
+        k.x = s.v1 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v1) >> 1) << 32) | (gbase + s.i1);
+        k.y = s.v2 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v2) >> 1) << 32) | (gbase + s.i2);
+        if (half == 1) merge_slot[row_in_block] = k;
+        asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kEpilogueWarps) : "memory");   // epilogue warps only
+        if (half == 0 && row < P.nq) {
+            const ulonglong2 o = merge_slot[row_in_block];
+            top2_insert(k.x, k.y, o.x);
+            top2_insert(k.x, k.y, o.y);
             unsigned long long* out = P.out + (long long)split * P.out_split_stride + ((long long)b * P.nq + row) * 2;
             *reinterpret_cast<ulonglong2*>(out) = k;
         }
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (cs > 1) ptx::cluster_sync();   // no CTA leaves while peers may still signal its barriers
+    else __syncthreads();
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
@@ -304,13 +353,59 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
 
 struct I8Plan {
     int ntiles, splits, tiles_per_split;
-    long long qblocks;
+    int cluster;                     // CTAs per cluster (query blocks sharing the B tiles)
+    long long qblocks;               // grid.x, rounded up to a multiple of `cluster`
 };
+
+int cluster_override()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HM_I8_CLUSTER");
+        v = e ? atoi(e) : 0;
+        if (v != 1 && v != 2 && v != 4) v = 0;
+    }
+    return v;
+}
+
+// CTAs that can be co-resident when launched as clusters of `cs` (1 CTA per SM; clusters of 4 cannot
+// use every SM of every GPC).  Queried once per cluster size; falls back to the SM count.
+int resident_ctas(int cs, int sm_count)
+{
+    static int cache[5] = {0, 0, 0, 0, 0};
+    if (cache[cs]) return cache[cs];
+    int v = sm_count;
+    if (cs > 1) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cs * 64, 1, 1);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSmemBytes;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)cs;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaFuncSetAttribute(hm_i8_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess &&
+            cudaOccupancyMaxActiveClusters(&n, hm_i8_knn2_kernel, &cfg) == cudaSuccess && n > 0)
+            v = n * cs;
+        else
+            cudaGetLastError();
+    }
+    cache[cs] = v;
+    return v;
+}
 
 I8Plan plan_i8(long long nq, long long nt, int batch, int sm_count)
 {
     I8Plan pl{};
-    pl.qblocks = ceil_div(nq, kBlockM);
+    const long long qb = ceil_div(nq, kBlockM);
+    pl.cluster = qb >= 4 ? 4 : (qb >= 2 ? 2 : 1);
+    if (cluster_override()) pl.cluster = cluster_override();
+    pl.qblocks = ceil_div(qb, pl.cluster) * pl.cluster;
+    sm_count = resident_ctas(pl.cluster, sm_count);
     pl.ntiles = (int)ceil_div(nt, kBlockN);
     const long long items = pl.qblocks * batch;
     // choose the split count minimising (waves) x (tiles per CTA + fixed prologue of ~2 tiles)
@@ -398,6 +493,7 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
     P.ntiles = pl.ntiles;
     P.train_base = train_base;
     P.error_flag = static_cast<int*>(ws);
+    P.q_blocks_valid = P.q_padded / kBlockM;
     const long long rows = nq * batch;
     unsigned long long* partials = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + 256);
     if (pl.splits > 1) {
@@ -411,10 +507,25 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
         set_error("grid too large");
         return HM_ERR_UNSUPPORTED;
     }
-    dim3 grid((unsigned)pl.qblocks, (unsigned)pl.splits, (unsigned)batch);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)pl.qblocks, (unsigned)pl.splits, (unsigned)batch);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)pl.cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
     profile_mark(true, stream);
-    hm_i8_knn2_kernel<<<grid, kThreads, kSmemBytes, stream>>>(P);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, hm_i8_knn2_kernel, P);
     profile_mark(false, stream);
+    if (le != cudaSuccess) {
+        set_error("cudaLaunchKernelEx(hm_i8_knn2_kernel, cluster %d) failed: %s", pl.cluster, cudaGetErrorString(le));
+        return HM_ERR_CUDA;
+    }
     HM_CUDA_CHECK(cudaGetLastError());
     if (pl.splits > 1) return launch_merge_top2(partials, pl.splits, rows, out, stream);
     return HM_OK;

@@ -78,6 +78,36 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                  : "memory");
 }
 
+// same, delivered to the same CTA-relative offset (data and mbarrier signal) of every CTA in cta_mask
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                                   uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;\n" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+        : "memory");
+}
+
+// ---- thread-block cluster ------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t cluster_nctarank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;\n" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync()   // all threads of all CTAs of the cluster
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 // ---- tensor memory ---------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols)   // whole warp
 {
@@ -102,6 +132,16 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
                  : "memory");
+}
+
+// same, arriving on the barrier at this CTA-relative offset in every CTA of cta_mask
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t cta_mask)
+{
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n" ::"r"(
+            smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
 }
 
 // D[tmem] (+)= A[smem] * B[smem], int8 x int8 -> int32, issued by ONE thread

@@ -1,0 +1,41 @@
+"""Condense an .ncu-rep (read here, no GPU needed) into the handful of numbers DESIGN.md cites."""
+import csv, io, subprocess, sys
+
+KEYS = [
+    "gpu__time_duration.sum", "sm__cycles_elapsed.avg.per_second", "launch__registers_per_thread",
+    "launch__grid_size", "launch__block_size",
+    "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+    "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_alu_realtime.avg.pct_of_peak_sustained_elapsed",
+    "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+    "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+    "sm__warps_active.avg.pct_of_peak_sustained_active",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "smsp__cycles_active.avg",
+]
+
+
+def raw(rep):
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(out)))
+    hdr, units = rows[0], rows[1]
+    return [{h: (v, u) for h, u, v in zip(hdr, units, vals)} for vals in rows[2:]]
+
+
+def main():
+    rep = sys.argv[1]
+    pats = sys.argv[2:]
+    for d in raw(rep):
+        print("== kernel:", d.get("Kernel Name", ("?",))[0], "grid", d.get("Grid Size", ("?",))[0],
+              "block", d.get("Block Size", ("?",))[0])
+        for h, (v, u) in d.items():
+            if (pats and any(p in h for p in pats)) or (not pats and h in KEYS):
+                print(f"  {h} = {v} {u}")
+
+
+if __name__ == "__main__":
+    main()
