@@ -1,29 +1,32 @@
 // Variant (b): tcgen05 kind::i8 GEMM on the +/-1 expansion of the descriptors.
 //
 // dot(a, b) over the +/-1 int8 images of two 256-bit descriptors is 256 - 2*H, so the
-// exact Hamming distance is H = (256 - dot) / 2 and "nearest" is "largest dot".  One
-// CTA owns a 128-query block (A operand, resident in shared memory) and streams
-// 256-row train tiles (B operand) through a bulk-async-copy ring; a single elected
-// thread issues 8 x tcgen05.mma (M=128, N=256, K=32 bytes) per tile into one of two
-// 256-column TMEM accumulators; four epilogue warps read the other accumulator with
-// tcgen05.ld (thread = query row, registers = train columns) and keep the running
-// top-2 in registers, so the 128x256 distance tile never leaves the SM.
+// exact Hamming distance is H = (256 - dot) / 2 and "nearest" is "largest dot".
 //
-// The +/-1 operands are 8x larger than the packed bits, so a single CTA streaming 64 KB of B
-// per 1024-cycle tile is bound by L2->SM bandwidth (ncu: 5.7 TB/s of xbar2l1tex reads at 31 %
-// tensor-pipe activity, profiles/r01a_*).  CTAs are therefore launched as thread-block clusters
-// of 2 or 4 neighbouring query blocks that share every train tile: each CTA fetches 1/CS of the
-// tile and multicasts it into the shared memory of all CS CTAs (cp.async.bulk ...
-// .multicast::cluster), and a stage is released by the multicast tcgen05.commit of all CS MMA
-// issuers.
+// One CTA owns 256 query rows (two 128-row A blocks, resident in shared memory, 64 KB) and
+// streams 128-row train tiles (B operand, 32 KB each) through a 4-deep bulk-async-copy ring.
+// Per tile a single elected thread issues 2 x 8 tcgen05.mma (M=128, N=128, K=32 bytes) into one of
+// two TMEM accumulator buffers (2 query blocks x 128 columns each; 512 columns in total); eight
+// epilogue warps (one per 32 query rows) read the other buffer with tcgen05.ld (thread = query
+// row, registers = train columns) and keep the running top-2 in registers, so the distance
+// tile never leaves the SM.
+//
+// Why this shape (ncu, profiles/r01a_* and r01b_*): the +/-1 operands are 8x larger than the
+// packed bits, so with 128 query rows per CTA each 1024-cycle tile needs 64 KB of B -- 10 TB/s of
+// L2->SM traffic at speed, and two 64 KB stages cannot cover the ~2500-cycle load latency
+// (tensor pipe 58 % active, long-scoreboard stalls).  256 query rows per CTA halve the bytes per
+// MMA cycle (32 B/clk/SM) and leave room for four stages (128 KB in flight).  Optionally CTAs are
+// launched as thread-block clusters of 2 or 4 query blocks that share every train tile: each CTA
+// fetches 1/CS of the tile and multicasts it (cp.async.bulk ... .multicast::cluster), and a stage
+// is released by the multicast tcgen05.commit of all CS MMA issuers.
 //
 // Replaces the same cv::batchDistance loop as hm_popc.cu
 // (/root/reference/feature_matchers.py:39 -> cv2.BFMatcher).
 //
 // Operands are "prepared" once by hm_prepare(): 256 bytes per descriptor, grouped in
 // blocks of 128 rows x 128 bytes (one K slab) laid out exactly as the UMMA K-major
-// SWIZZLE_128B shared-memory image, so a block is one contiguous 16 KB bulk copy
-// (cp.async.bulk / UBLKCP) with no tensor map.
+// SWIZZLE_128B shared-memory image; a 128-row block is [slab 0 | slab 1] = 32 contiguous KB, so
+// a train tile is ONE bulk copy (cp.async.bulk / UBLKCP) with no tensor map.
 #include <stdlib.h>
 
 #include "hm_common.cuh"
@@ -33,20 +36,20 @@ namespace hm {
 
 namespace {
 
-constexpr int kBlockM = 128;                 // queries per CTA
-constexpr int kBlockN = 256;                 // train rows per tile
-constexpr int kRowBlock = 128;               // rows per prepared block
+constexpr int kRowBlock = 128;               // rows per prepared block = UMMA M = tile N
+constexpr int kMBlocks = 2;                  // A blocks per CTA
+constexpr int kBlockM = kRowBlock * kMBlocks;   // 256 queries per CTA
+constexpr int kBlockN = kRowBlock;           // train rows per tile
 constexpr int kSlabBytes = kRowBlock * 128;  // 16 KB: 128 rows x 128 bytes of K
-constexpr int kRowBlockBytes = 2 * kSlabBytes;
+constexpr int kRowBlockBytes = 2 * kSlabBytes;  // 32 KB: one prepared row block
 constexpr int kPadRows = HM_PREPARED_TILE_ROWS;
-constexpr int kStages = 2;
-constexpr int kABytes = 2 * kSlabBytes;      // 32 KB
-constexpr int kBStageBytes = 4 * kSlabBytes; // 64 KB
-constexpr int kTmemCols = 512;
-constexpr int kEpilogueWarps = 8;            // two per TMEM lane quarter: each takes one 128-column half
+constexpr int kStages = 4;
+constexpr int kABytes = kMBlocks * kRowBlockBytes;   // 64 KB
+constexpr int kBStageBytes = kRowBlockBytes;         // 32 KB
+constexpr int kTmemCols = 512;               // 2 buffers x 2 query blocks x 128 columns
+constexpr int kEpilogueWarps = 4 * kMBlocks; // one per 32 query rows
 constexpr int kThreads = 64 + 32 * kEpilogueWarps;   // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
-constexpr int kMergeBytes = kBlockM * 16;    // upper-half partial top-2 (two 64-bit keys per row)
-constexpr int kSmemBytes = 1024 + kABytes + kStages * kBStageBytes + 256 + kMergeBytes;
+constexpr int kSmemBytes = 1024 + kABytes + kStages * kBStageBytes + 256;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
 static_assert(kPadRows % kBlockN == 0 && kPadRows % kBlockM == 0, "prepared padding must cover whole tiles");
@@ -101,14 +104,23 @@ struct I8Params {
     const uint8_t* tprep;            // [batch][t_padded][256]
     long long nq, nt;
     long long q_padded, t_padded;
-    int tiles_per_split;             // train tiles (256 rows) per split
+    int tiles_per_split;             // train tiles (128 rows) per split
     int ntiles;                      // total train tiles
     unsigned long long train_base;
     unsigned long long* out;         // [split][batch][nq][2]
     long long out_split_stride;      // keys
     int* error_flag;
-    long long q_blocks_valid;        // 128-row blocks present in qprep (CTAs beyond it are cluster padding)
+    long long q_blocks_valid;        // 256-row blocks present in qprep (CTAs beyond it are cluster padding)
+    long long* trace;                // development aid (HM_I8_TRACE): per-tile clock64 stamps of CTA 0, else null
 };
+
+constexpr int kTraceTiles = 96;
+constexpr int kTraceSlots = 8;
+__device__ __forceinline__ void trace_mark(const I8Params& P, int tile, int slot)
+{
+    if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile < kTraceTiles)
+        P.trace[tile * kTraceSlots + slot] = clock64();
+}
 
 struct Top2 {
     int v1, v2;                      // best / second-best dot (larger = closer)
@@ -124,6 +136,14 @@ __device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity, int
             __trap();
         }
     }
+}
+
+#define HM_R8(a, o) "+r"(a[o]), "+r"(a[o + 1]), "+r"(a[o + 2]), "+r"(a[o + 3]), "+r"(a[o + 4]), "+r"(a[o + 5]), "+r"(a[o + 6]), "+r"(a[o + 7])
+#define HM_R32(a) HM_R8(a, 0), HM_R8(a, 8), HM_R8(a, 16), HM_R8(a, 24)
+// one wait for four outstanding 32-column loads (128 registers pinned behind it)
+__device__ __forceinline__ void tmem_ld_fence4(uint32_t (&a)[32], uint32_t (&b)[32], uint32_t (&c)[32], uint32_t (&d)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(a), HM_R32(b), HM_R32(c), HM_R32(d) : : "memory");
 }
 
 __device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32])
@@ -183,20 +203,20 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* smem_a = smem;
-    uint8_t* smem_b = smem + kABytes;
+    uint8_t* smem_a = smem;                      // [query block 0: slab0 | slab1][query block 1: slab0 | slab1]
+    uint8_t* smem_b = smem + kABytes;            // kStages x [slab0 | slab1] of one 128-row train tile
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + kStages * kBStageBytes);
     uint64_t* full_bar = bars;                   // [kStages]  bulk copies landed
     uint64_t* empty_bar = bars + kStages;        // [kStages]  MMAs reading the stage retired
     uint64_t* a_full_bar = bars + 2 * kStages;   // [1]
-    uint64_t* tmem_full_bar = bars + 2 * kStages + 1;   // [2] accumulator complete
-    uint64_t* tmem_empty_bar = bars + 2 * kStages + 3;  // [2] accumulator drained by the epilogue
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 5);
-    ulonglong2* merge_slot = reinterpret_cast<ulonglong2*>(smem + kABytes + kStages * kBStageBytes + 256);
+    // accumulator units: u = buffer * kMBlocks + query block, 128 TMEM columns each
+    uint64_t* tmem_full_bar = bars + 2 * kStages + 1;                   // [4] unit complete
+    uint64_t* tmem_empty_bar = bars + 2 * kStages + 1 + 2 * kMBlocks;   // [4] unit drained by its epilogue warps
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1 + 4 * kMBlocks);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int qb = blockIdx.x;
+    const int qb = blockIdx.x;                   // 256-row query block
     const int split = blockIdx.y;
     const int b = blockIdx.z;
 
@@ -215,9 +235,9 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
             ptx::mbar_init(&empty_bar[i], cs);           // one multicast commit per CTA of the cluster
         }
         ptx::mbar_init(a_full_bar, 1);
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 2 * kMBlocks; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], kEpilogueWarps);   // one arrival per epilogue warp
+            ptx::mbar_init(&tmem_empty_bar[i], 4);       // one arrival per epilogue warp of that query block
         }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -234,109 +254,108 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
     if (warp == 0) {
         // ===== producer: bulk async copies global -> shared =====
         if (lane == 0) {
-            const uint8_t* qsrc = P.qprep + ((long long)b * P.q_padded + (long long)qb * kBlockM) * HM_PREPARED_ROW_BYTES;
             if (has_a) {
+                const uint8_t* qsrc = P.qprep + ((long long)b * P.q_padded + (long long)qb * kBlockM) * HM_PREPARED_ROW_BYTES;
                 ptx::mbar_arrive_expect_tx(a_full_bar, kABytes);
-                ptx::bulk_g2s(smem_a, qsrc, kABytes, a_full_bar);      // [slab0 | slab1] of one row block
+                ptx::bulk_g2s(smem_a, qsrc, kABytes, a_full_bar);       // two consecutive row blocks, 64 KB
             }
             const uint8_t* tsrc = P.tprep + (long long)b * P.t_padded * HM_PREPARED_ROW_BYTES;
+            const uint32_t piece = kBStageBytes / cs;     // this CTA fetches 1/cs of every tile and multicasts it
             for (int i = 0; i < my_tiles; ++i) {
                 const int stage = i % kStages;
                 const uint32_t use = i / kStages;
                 bounded_wait(&empty_bar[stage], (use & 1) ^ 1, P.error_flag);
+                trace_mark(P, i, 0);                      // producer: stage free, copy issued
                 ptx::mbar_arrive_expect_tx(&full_bar[stage], kBStageBytes);
-                uint8_t* dst = smem_b + stage * kBStageBytes;
-                const uint8_t* src = tsrc + (long long)(tile_begin + i) * 2 * kRowBlockBytes;
-                // stage image: [slab0: rows 0-127 | rows 128-255][slab1: rows 0-127 | rows 128-255];
-                // piece p (16 KB) = row block (p & 1), slab (p >> 1).  This CTA fetches 4/cs pieces and
-                // multicasts them; the other pieces arrive from its cluster peers.
-                const int per = 4 / (int)cs;
-                for (int p = (int)crank * per; p < ((int)crank + 1) * per; ++p) {
-                    const uint8_t* psrc = src + (p & 1) * kRowBlockBytes + (p >> 1) * kSlabBytes;
-                    if (cs > 1) ptx::bulk_g2s_multicast(dst + p * kSlabBytes, psrc, kSlabBytes, &full_bar[stage], cmask);
-                    else        ptx::bulk_g2s(dst + p * kSlabBytes, psrc, kSlabBytes, &full_bar[stage]);
-                }
+                uint8_t* dst = smem_b + stage * kBStageBytes + crank * piece;
+                const uint8_t* src = tsrc + (long long)(tile_begin + i) * kRowBlockBytes + crank * piece;
+                if (cs > 1) ptx::bulk_g2s_multicast(dst, src, piece, &full_bar[stage], cmask);
+                else        ptx::bulk_g2s(dst, src, piece, &full_bar[stage]);
             }
         }
     } else if (warp == 1) {
         // ===== MMA issuer =====
-        constexpr uint32_t idesc = ptx::make_i8_idesc(kBlockM, kBlockN);
+        constexpr uint32_t idesc = ptx::make_i8_idesc(kRowBlock, kBlockN);
         const uint32_t a_addr = ptx::smem_u32(smem_a);
         const uint32_t b_addr = ptx::smem_u32(smem_b);
         if (has_a) bounded_wait(a_full_bar, 0, P.error_flag);
         for (int i = 0; i < my_tiles; ++i) {
             const int stage = i % kStages;
             const uint32_t use = i / kStages;
-            const int acc = i & 1;
-            const uint32_t acc_use = i >> 1;
-            bounded_wait(&tmem_empty_bar[acc], (acc_use & 1) ^ 1, P.error_flag);
+            const int buf = i & 1;
+            const uint32_t buf_use = i >> 1;
             bounded_wait(&full_bar[stage], use & 1, P.error_flag);
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
+            if (lane == 0) trace_mark(P, i, 2);           // MMA: operands landed
 #pragma unroll
-                for (int s = 0; s < 2; ++s) {
+            for (int m = 0; m < kMBlocks; ++m) {
+                const int unit = buf * kMBlocks + m;
+                bounded_wait(&tmem_empty_bar[unit], (buf_use & 1) ^ 1, P.error_flag);
+                if (lane == 0 && m == 0) trace_mark(P, i, 1);   // MMA: accumulator unit free
+                ptx::tc_fence_after();
+                if (ptx::elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + s * kSlabBytes + k * 32);
-                        const uint64_t db = ptx::make_kmajor_sw128_desc(b_addr + stage * kBStageBytes +
-                                                                        s * 2 * kSlabBytes + k * 32);
-                        ptx::mma_i8_ss(tmem_base + acc * kBlockN, da, db, idesc, (s | k) != 0);
+                    for (int s = 0; s < 2; ++s) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const uint64_t da = ptx::make_kmajor_sw128_desc(a_addr + m * kRowBlockBytes + s * kSlabBytes + k * 32);
+                            const uint64_t db = ptx::make_kmajor_sw128_desc(b_addr + stage * kBStageBytes + s * kSlabBytes + k * 32);
+                            ptx::mma_i8_ss(tmem_base + unit * kBlockN, da, db, idesc, (s | k) != 0);
+                        }
+                    }
+                    ptx::tc_commit(&tmem_full_bar[unit]);     // this query block's accumulator is ready
+                    if (m == kMBlocks - 1) {
+                        // smem stage reusable (by every producer of the cluster) once these MMAs retire
+                        if (cs > 1) ptx::tc_commit_multicast(&empty_bar[stage], cmask);
+                        else        ptx::tc_commit(&empty_bar[stage]);
                     }
                 }
-                // smem stage reusable (by every producer of the cluster) once these MMAs retire
-                if (cs > 1) ptx::tc_commit_multicast(&empty_bar[stage], cmask);
-                else        ptx::tc_commit(&empty_bar[stage]);
-                ptx::tc_commit(&tmem_full_bar[acc]);      // accumulator ready for the epilogue
+                __syncwarp();
             }
             __syncwarp();
         }
     } else {
         // ===== epilogue: TMEM -> registers, running top-2 per query row =====
-        // Warps 2..5 scan columns [0,128) of every tile, warps 6..9 columns [128,256) of the same rows,
-        // so each SM sub-partition has two epilogue warps to overlap TMEM loads with the scan.
         const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
-        const int half = (warp - 2) >> 2;                 // which 128-column half of the tile
-        const int row_in_block = quarter * 32 + lane;
-        const long long row = (long long)qb * kBlockM + row_in_block;
+        const int mblk = (warp - 2) >> 2;                 // which 128-row query block of the CTA
+        const long long row = (long long)qb * kBlockM + mblk * kRowBlock + quarter * 32 + lane;
         Top2 s;
         s.v1 = s.v2 = INT_MIN;
         s.i1 = s.i2 = 0;
         const long long first_row = (long long)tile_begin * kBlockN;
         const unsigned limit = (unsigned)min((long long)my_tiles * kBlockN, P.nt - first_row);
-        constexpr int kChunks = kBlockN / 32 / 2;         // chunks of 32 columns per warp per tile
         for (int i = 0; i < my_tiles; ++i) {
-            const int acc = i & 1;
-            const uint32_t acc_use = i >> 1;
-            bounded_wait(&tmem_full_bar[acc], acc_use & 1, P.error_flag);
+            const int buf = i & 1;
+            const uint32_t buf_use = i >> 1;
+            const int unit = buf * kMBlocks + mblk;
+            bounded_wait(&tmem_full_bar[unit], buf_use & 1, P.error_flag);
+            if (warp == 2 && lane == 0) trace_mark(P, i, 3);   // epilogue: accumulator complete
+            if (warp == 9 && lane == 0) trace_mark(P, i, 5);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * kBlockN + half * (kBlockN / 2);
-            const unsigned colbase = (unsigned)i * kBlockN + half * (kBlockN / 2);
-            uint32_t ra[32], rb[32];
-            ptx::tmem_ld_32x32(taddr, ra);
-#pragma unroll 1   // keep the loop body (two chunks) resident in the instruction cache
-            for (int c = 0; c < kChunks; c += 2) {
-                tmem_ld_fence(ra);
-                ptx::tmem_ld_32x32(taddr + (c + 1) * 32, rb);
-                scan_chunk(ra, colbase + c * 32, limit, s);
-                tmem_ld_fence(rb);
-                if (c + 2 < kChunks) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, ra);
-                scan_chunk(rb, colbase + (c + 1) * 32, limit, s);
-            }
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + unit * kBlockN;
+            const unsigned colbase = (unsigned)i * kBlockN;
+            // all four 32-column loads are issued before the first scan so their latencies overlap
+            uint32_t r0[32], r1[32], r2[32], r3[32];
+            ptx::tmem_ld_32x32(taddr, r0);
+            ptx::tmem_ld_32x32(taddr + 32, r1);
+            ptx::tmem_ld_32x32(taddr + 64, r2);
+            ptx::tmem_ld_32x32(taddr + 96, r3);
+            tmem_ld_fence4(r0, r1, r2, r3);
+            // the accumulator unit is in registers: release it before the scan
             ptx::tc_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
+            scan_chunk(r0, colbase, limit, s);
+            scan_chunk(r1, colbase + 32, limit, s);
+            scan_chunk(r2, colbase + 64, limit, s);
+            scan_chunk(r3, colbase + 96, limit, s);
+            if (warp == 2 && lane == 0) trace_mark(P, i, 4);   // epilogue: buffer released
+            if (warp == 9 && lane == 0) trace_mark(P, i, 6);
         }
-        // widen to 64-bit global keys; the upper-half warps hand theirs over through shared memory
-        const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
-        ulonglong2 k;
-        k.x = s.v1 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v1) >> 1) << 32) | (gbase + s.i1);
-        k.y = s.v2 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v2) >> 1) << 32) | (gbase + s.i2);
-        if (half == 1) merge_slot[row_in_block] = k;
-        asm volatile("bar.sync 1, %0;\n" ::"n"(32 * kEpilogueWarps) : "memory");   // epilogue warps only
-        if (half == 0 && row < P.nq) {
-            const ulonglong2 o = merge_slot[row_in_block];
-            top2_insert(k.x, k.y, o.x);
-            top2_insert(k.x, k.y, o.y);
+        if (row < P.nq) {
+            const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
+            ulonglong2 k;
+            k.x = s.v1 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v1) >> 1) << 32) | (gbase + s.i1);
+            k.y = s.v2 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v2) >> 1) << 32) | (gbase + s.i2);
             unsigned long long* out = P.out + (long long)split * P.out_split_stride + ((long long)b * P.nq + row) * 2;
             *reinterpret_cast<ulonglong2*>(out) = k;
         }
@@ -402,13 +421,13 @@ I8Plan plan_i8(long long nq, long long nt, int batch, int sm_count)
 {
     I8Plan pl{};
     const long long qb = ceil_div(nq, kBlockM);
-    pl.cluster = qb >= 4 ? 4 : (qb >= 2 ? 2 : 1);
+    pl.cluster = 1;
     if (cluster_override()) pl.cluster = cluster_override();
     pl.qblocks = ceil_div(qb, pl.cluster) * pl.cluster;
     sm_count = resident_ctas(pl.cluster, sm_count);
     pl.ntiles = (int)ceil_div(nt, kBlockN);
     const long long items = pl.qblocks * batch;
-    // choose the split count minimising (waves) x (tiles per CTA + fixed prologue of ~2 tiles)
+    // choose the split count minimising (waves) x (tiles per CTA + fixed prologue worth ~4 tiles)
     long long best_cost = -1;
     int best = 1;
     const int max_splits = (int)min((long long)pl.ntiles, 4096ll);
@@ -416,7 +435,7 @@ I8Plan plan_i8(long long nq, long long nt, int batch, int sm_count)
         const long long tps = ceil_div(pl.ntiles, s);
         const long long real_s = ceil_div(pl.ntiles, tps);
         const long long waves = ceil_div(items * real_s, sm_count);
-        const long long cost = waves * (tps + 2);
+        const long long cost = waves * (tps + 4);
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = s;
@@ -494,6 +513,11 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
     P.train_base = train_base;
     P.error_flag = static_cast<int*>(ws);
     P.q_blocks_valid = P.q_padded / kBlockM;
+    const char* trace_path = getenv("HM_I8_TRACE");
+    if (trace_path) {
+        HM_CUDA_CHECK(cudaMalloc(&P.trace, sizeof(long long) * kTraceTiles * kTraceSlots));
+        HM_CUDA_CHECK(cudaMemset(P.trace, 0, sizeof(long long) * kTraceTiles * kTraceSlots));
+    }
     const long long rows = nq * batch;
     unsigned long long* partials = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + 256);
     if (pl.splits > 1) {
@@ -527,6 +551,23 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
         return HM_ERR_CUDA;
     }
     HM_CUDA_CHECK(cudaGetLastError());
+    if (trace_path) {   // development aid: dump the per-tile time stamps of CTA 0
+        static long long host[kTraceTiles * kTraceSlots];
+        HM_CUDA_CHECK(cudaStreamSynchronize(stream));
+        HM_CUDA_CHECK(cudaMemcpy(host, P.trace, sizeof(host), cudaMemcpyDeviceToHost));
+        cudaFree(P.trace);
+        if (FILE* f = fopen(trace_path, "w")) {
+            fprintf(f, "# tile producer_issue mma_buf_free mma_operands epi2_full epi2_release epi9_full epi9_release (cycles since first stamp); tiles/CTA=%d splits=%d cluster=%d\n",
+                    pl.tiles_per_split, pl.splits, pl.cluster);
+            long long t0 = host[0];
+            for (int i = 0; i < kTraceTiles; ++i) {
+                fprintf(f, "%d", i);
+                for (int k = 0; k < 7; ++k) fprintf(f, " %lld", host[i * kTraceSlots + k] ? host[i * kTraceSlots + k] - t0 : -1);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     if (pl.splits > 1) return launch_merge_top2(partials, pl.splits, rows, out, stream);
     return HM_OK;
 }

@@ -1,0 +1,17 @@
+"""Development aid: dump the per-tile pipeline time stamps of CTA 0 of the tensor-core kernel."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["HM_I8_TRACE"] = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/trace_i8.txt"
+import torch
+from slam_experiments_b200 import _native as nat, synth
+nq, nt = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else (65536, 65536)
+q = torch.from_numpy(synth.uniform(nq, 1)).cuda()
+t = torch.from_numpy(synth.uniform(nt, 2)).cuda()
+os.environ.pop("HM_I8_TRACE")
+for _ in range(2):
+    nat.knn2_keys(q, t, variant="i8")
+torch.cuda.synchronize()
+os.environ["HM_I8_TRACE"] = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/trace_i8.txt"
+nat.knn2_keys(q, t, variant="i8")
+torch.cuda.synchronize()
+print(open(os.environ["HM_I8_TRACE"]).read())
