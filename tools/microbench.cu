@@ -102,6 +102,125 @@ __global__ void __launch_bounds__(128, 1) mma_kernel(int iters, long long* cycle
     if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(slot, 512); }
 }
 
+// ---------------------------------------------------------------- MMA issue patterns
+// issuers: 1 or 2 warps, each issuing groups of 8 MMAs (N=128) into its own accumulators;
+// commit_every: 0 = one commit at the end, 8 = a tcgen05.commit (to a scratch mbarrier) after every group
+__global__ void __launch_bounds__(128, 1) mma_pattern_kernel(int iters, int issuers, int commit_every, long long* cycles)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t slot;
+    __shared__ __align__(8) uint64_t bar[2], scratch[2];
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    for (int i = threadIdx.x; i < (65536 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01FF01FFu;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) { ptx::tmem_alloc(&slot, 512); ptx::tmem_relinquish(); }
+    if (threadIdx.x == 32) {
+        ptx::mbar_init(&bar[0], 1); ptx::mbar_init(&bar[1], 1);
+        ptx::mbar_init(&scratch[0], 1 << 20); ptx::mbar_init(&scratch[1], 1 << 20);
+        ptx::fence_barrier_init();
+    }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 1 || (warp == 2 && issuers == 2)) {
+        const int m = warp - 1;
+        const uint32_t a = ptx::smem_u32(smem) + m * 32768, b = ptx::smem_u32(smem) + 65536;
+        constexpr uint32_t idesc = ptx::make_i8_idesc(128, 128);
+        long long t0 = clock64();
+        if (ptx::elect_one()) {
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::mma_i8_ss(slot + ((it & 1) * 2 + m) * 128, ptx::make_kmajor_sw128_desc(a + s * 16384 + k * 32),
+                                       ptx::make_kmajor_sw128_desc(b + s * 16384 + k * 32), idesc, (s | k) != 0);
+                if (commit_every) { ptx::tc_commit(&scratch[m]); ptx::tc_commit(&scratch[m]); }
+            }
+            ptx::tc_commit(&bar[m]);
+        }
+        __syncwarp();
+        ptx::mbar_wait(&bar[m], 0);
+        long long t1 = clock64();
+        if ((threadIdx.x & 31) == 0) cycles[blockIdx.x * 2 + m] = t1 - t0;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(slot, 512); }
+}
+
+// ---------------------------------------------------------------- MMA with concurrent shared-memory writes / TMEM reads
+// mode bit 0: a second warp streams bulk copies (UBLKCP) into a separate smem region while the MMAs run
+// mode bit 1: four more warps loop on tcgen05.ld of the other accumulator half
+__global__ void __launch_bounds__(256, 1) mma_interference_kernel(int iters, int mode, const uint8_t* gsrc, long long* cycles,
+                                                                  unsigned* sink, long long* copied)
+{
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint32_t slot;
+    __shared__ __align__(8) uint64_t bar, cbar[2];
+    __shared__ volatile int done;
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    for (int i = threadIdx.x; i < (32768 + 32768) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x01FF01FFu;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) { ptx::tmem_alloc(&slot, 512); ptx::tmem_relinquish(); }
+    if (threadIdx.x == 32) { ptx::mbar_init(&bar, 1); ptx::mbar_init(&cbar[0], 1); ptx::mbar_init(&cbar[1], 1); ptx::fence_barrier_init(); done = 0; }
+    ptx::fence_proxy_async();
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    if (warp == 1) {
+        const uint32_t a = ptx::smem_u32(smem), b = a + 32768;
+        constexpr uint32_t idesc = ptx::make_i8_idesc(128, 128);
+        long long t0 = clock64();
+        if (ptx::elect_one()) {
+            for (int it = 0; it < iters; ++it) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        ptx::mma_i8_ss(slot + (it & 1) * 128, ptx::make_kmajor_sw128_desc(a + s * 16384 + k * 32),
+                                       ptx::make_kmajor_sw128_desc(b + s * 16384 + k * 32), idesc, (s | k) != 0);
+            }
+            ptx::tc_commit(&bar);
+        }
+        __syncwarp();
+        ptx::mbar_wait(&bar, 0);
+        long long t1 = clock64();
+        if (threadIdx.x == 32) { cycles[blockIdx.x] = t1 - t0; done = 1; }
+    } else if (warp == 2 && (mode & 1)) {
+        if (threadIdx.x == 64) {
+            uint8_t* dst = smem + 65536;
+            long long n = 0;
+            const uint8_t* src = gsrc + (size_t)blockIdx.x * (1 << 20);
+            for (int it = 0; !done; ++it) {
+                const int sgn = it & 1;
+                ptx::mbar_arrive_expect_tx(&cbar[sgn], 32768);
+                ptx::bulk_g2s(dst + sgn * 32768, src + (size_t)(it & 31) * 32768, 32768, &cbar[sgn]);
+                if (it > 0) ptx::mbar_wait(&cbar[sgn ^ 1], ((it - 1) >> 1) & 1);
+                n += 32768;
+            }
+            copied[blockIdx.x] = n;
+        }
+    } else if (warp >= 4 && (mode & 2)) {
+        uint32_t r[32];
+        unsigned acc = 0;
+        const uint32_t base = slot + ((uint32_t)((warp & 3) * 32) << 16) + 256;
+        while (!done) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                ptx::tmem_ld_32x32(base + c * 32, r);
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" : "+r"(r[0]), "+r"(r[31]) :: "memory");
+                acc += r[0] ^ r[31];
+            }
+        }
+        sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) { ptx::tc_fence_after(); ptx::tmem_dealloc(slot, 512); }
+}
+
 int main()
 {
     int dev = 0, sms = 0, khz = 0;
@@ -165,6 +284,46 @@ int main()
             double macs = (double)iters * 8 * 128 * n * 32;
             printf(", \"mma_i8_n%d_cycles_per_mma\": %.1f, \"mma_i8_n%d_mac_per_clk_per_sm\": %.0f, \"mma_i8_n%d_chip_tops\": %.1f",
                    n, (double)h / (iters * 8), n, macs / (double)h, n, 2.0 * macs * sms / (ms * 1e-3) / 1e12);
+        }
+    }
+    // issue patterns
+    {
+        const int iters = 4000;
+        const int smem_bytes = 65536 + 32768 + 2048;
+        CK(cudaFuncSetAttribute(mma_pattern_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        for (int issuers = 1; issuers <= 2; ++issuers)
+            for (int ce = 0; ce <= 8; ce += 8) {
+                for (int rep = 0; rep < 2; ++rep) {
+                    mma_pattern_kernel<<<sms, 128, smem_bytes>>>(iters, issuers, ce, cyc);
+                    CK(cudaDeviceSynchronize());
+                }
+                long long h[2];
+                CK(cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+                printf(", \"mma_pattern_issuers%d_commit%d_cycles_per_mma\": %.1f", issuers, ce,
+                       (double)h[0] / (iters * 8 * issuers));
+            }
+    }
+    // MMA N=128 with concurrent smem writes / TMEM reads
+    {
+        const int iters = 4000;
+        const int smem_bytes = 65536 + 65536 + 2048;
+        uint8_t* gsrc;
+        long long* copied;
+        CK(cudaMalloc(&gsrc, (size_t)sms << 20));
+        CK(cudaMemset(gsrc, 1, (size_t)sms << 20));
+        CK(cudaMalloc(&copied, sizeof(long long) * sms));
+        CK(cudaFuncSetAttribute(mma_interference_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        for (int mode = 0; mode < 4; ++mode) {
+            CK(cudaMemset(copied, 0, sizeof(long long) * sms));
+            for (int rep = 0; rep < 2; ++rep) {
+                mma_interference_kernel<<<sms, 256, smem_bytes>>>(iters, mode, gsrc, cyc, out, copied);
+                CK(cudaDeviceSynchronize());
+            }
+            long long h, n;
+            CK(cudaMemcpy(&h, cyc, sizeof(h), cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy(&n, copied, sizeof(n), cudaMemcpyDeviceToHost));
+            printf(", \"mma_n128_mode%d_cycles_per_mma\": %.1f, \"mma_n128_mode%d_copy_bytes_per_clk\": %.1f", mode,
+                   (double)h / (iters * 8), mode, (double)n / (double)h);
         }
     }
     printf("}\n");
