@@ -65,7 +65,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -191,6 +191,8 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -281,14 +283,17 @@ def run_b200(args):
                     "note": f"int8 ops (512/pair); peak = 2 x bf16_tflops_sustained of {peak_src} "
                             "(kind::i8 issues at twice the bf16 rate)",
                     "kernel_ms": kern_ms_max, "pairs_per_launch": local_pairs,
+                    "frac_of_mma_issue_peak": achieved / 4569.0,
+                    "mma_issue_peak_note": "4569 int8 TOP/s = tcgen05.mma kind::i8 issue loop at 1965 MHz "
+                                           "(tools/microbench.cu, profiles/r01_microbench_b200.json)",
                     "hbm_gbs": (nt_local * 256 + NQ * 256) / (kern_ms_max * 1e-3) / 1e9}
     else:
         sm = nat.sm_count()
         achieved = local_pairs * POPC_PER_PAIR / (kern_ms_max * 1e-3) / 1e12
         peak = sm * 16 * peaks["sm_max_mhz"] * 1e6 / 1e12
-        roofline = {"bound": "tensor", "kernel": "hm_popc_knn2_kernel", "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                    "note": "POPC issue roofline (not tensor): T-popc/s, 8 per pair; peak = SMs x 16/clk x sm_max_mhz",
+        roofline = {"bound": "popc", "kernel": "hm_popc_knn2_kernel", "achieved": achieved, "peak": peak,
+                    "unit": "Tpopc/s", "frac": achieved / peak, "traffic": None,
+                    "note": "POPC issue roofline: 8 POPC per pair; peak = SMs x 16/clk (measured 15.7) x sm_max_mhz",
                     "kernel_ms": kern_ms_max, "pairs_per_launch": local_pairs}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
@@ -335,7 +340,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="auto", choices=["auto", "popc", "i8"])
