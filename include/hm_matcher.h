@@ -152,6 +152,15 @@ HM_API void hm_context_destroy(hm_context* ctx);
 HM_API int hm_knn2_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
                         const uint8_t* train_host, int64_t nt, uint64_t* out_keys_host, int variant);
 
+/* numpy-in / numpy-out twin of hm_match_fused (batch = 1): H2D of both descriptor sets through
+ * pinned staging, k-NN (+ swapped pass with HM_FLAG_MUTUAL), filter, D2H, one synchronisation.
+ * out_q/out_t/out_d_host[nq] int32, *out_count_host = number of matches (ordered by queryIdx).
+ * This is the call behind BruteForceFeatureMatcher.match() for numpy inputs. */
+HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq, int64_t q_stride,
+                         const uint8_t* train_host, int64_t nt, int64_t t_stride,
+                         unsigned flags, const uint16_t* ratio_lut_host, double dist_threshold, int variant,
+                         int32_t* out_q_host, int32_t* out_t_host, int32_t* out_d_host, int32_t* out_count_host);
+
 #ifdef __cplusplus
 }
 #endif

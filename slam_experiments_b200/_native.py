@@ -32,7 +32,7 @@ EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
     "hm_knn2", "hm_knn2_batched", "hm_prepared_bytes", "hm_prepare", "hm_knn2_prepared",
     "hm_merge_top2", "hm_filter_matches", "hm_match_fused",
-    "hm_context_create", "hm_context_destroy", "hm_knn2_host",
+    "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host",
 )
 
 
@@ -79,6 +79,8 @@ def _declare(L):
     L.hm_context_destroy.argtypes = [vp]
     L.hm_knn2_host.restype = ci
     L.hm_knn2_host.argtypes = [vp, vp, i64, vp, i64, vp, ci]
+    L.hm_match_host.restype = ci
+    L.hm_match_host.argtypes = [vp, vp, i64, i64, vp, i64, i64, cu, vp, c.c_double, ci, vp, vp, vp, vp]
 
 
 def lib():
@@ -247,6 +249,16 @@ def ratio_lut(ratio: float) -> np.ndarray:
     return lut
 
 
+_lut_cache = {}
+
+
+def _ratio_lut_cached(ratio: float) -> np.ndarray:
+    lut = _lut_cache.get(ratio)
+    if lut is None:
+        lut = _lut_cache[ratio] = ratio_lut(ratio)
+    return lut
+
+
 def match_fused(query: torch.Tensor, train: torch.Tensor, ratio: Optional[float] = None,
                 cross_check: bool = False, dist_threshold: Optional[float] = None, variant="auto",
                 want_keys: bool = False):
@@ -336,6 +348,33 @@ class HostContext:
         check(lib().hm_knn2_host(self._h, q.ctypes.data, q.shape[0], t.ctypes.data, t.shape[0],
                                  out.ctypes.data, variant_id(variant)), "hm_knn2_host")
         return out
+
+    def match(self, query: np.ndarray, train: np.ndarray, ratio: Optional[float] = None,
+              cross_check: bool = False, dist_threshold: Optional[float] = None, variant="auto"):
+        """``hm_match_host``: fused pipeline, numpy in -> ``(q, t, d)`` int32 arrays out."""
+        q, t = query, train
+        if q.strides[1] != 1 or q.strides[0] < DESC_BYTES:
+            q = np.ascontiguousarray(q)
+        if t.strides[1] != 1 or t.strides[0] < DESC_BYTES:
+            t = np.ascontiguousarray(t)
+        nq = q.shape[0]
+        flags, lut_ptr, lut, thr = 0, None, None, 0.0
+        if ratio is not None:
+            flags |= FLAG_RATIO
+            lut = _ratio_lut_cached(float(ratio))
+            lut_ptr = lut.ctypes.data
+        if cross_check:
+            flags |= FLAG_MUTUAL
+        if dist_threshold:
+            flags |= FLAG_DIST_THRESHOLD
+            thr = float(dist_threshold)
+        out = np.empty((3, max(nq, 1)), dtype=np.int32)
+        cnt = ctypes.c_int32(0)
+        check(lib().hm_match_host(self._h, q.ctypes.data, nq, q.strides[0], t.ctypes.data, t.shape[0], t.strides[0],
+                                  flags, lut_ptr, thr, variant_id(variant), out[0].ctypes.data, out[1].ctypes.data,
+                                  out[2].ctypes.data, ctypes.byref(cnt)), "hm_match_host")
+        n = cnt.value
+        return out[0, :n], out[1, :n], out[2, :n]
 
     def close(self):
         if self._h:

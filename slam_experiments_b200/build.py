@@ -33,7 +33,26 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+FAST_SRC = os.path.join(CSRC, "hmfast.c")
+FAST_SO = os.path.join(HERE, "_hmfast.so")
+
+
+def build_hmfast(force: bool = False) -> str:
+    """Host-side helper (CPython C API, gcc): bulk cv2.DMatch construction.  Optional: the Python
+    side falls back to calling the DMatch type when it is missing."""
+    import sysconfig
+    if not force and os.path.exists(FAST_SO) and os.path.getmtime(FAST_SO) >= os.path.getmtime(FAST_SRC):
+        return FAST_SO
+    inc = sysconfig.get_paths()["include"]
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-I", inc, "-o", FAST_SO, FAST_SRC])
+    return FAST_SO
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
+    try:
+        build_hmfast(force)
+    except Exception as e:  # pragma: no cover - optional accelerator
+        print(f"warning: _hmfast not built ({e}); DMatch construction falls back to Python", file=sys.stderr)
     if not force and not is_stale():
         return SO
     cmd = [

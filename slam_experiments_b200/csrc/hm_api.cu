@@ -446,4 +446,71 @@ HM_API int hm_knn2_host(hm_context* ctx, const uint8_t* query_host, int64_t nq, 
     return HM_OK;
 }
 
+static int ctx_reserve(hm_context* ctx, size_t dneed, size_t hneed)
+{
+    if (ctx->d_cap < dneed) {
+        if (ctx->d_buf) cudaFree(ctx->d_buf);
+        ctx->d_buf = nullptr; ctx->d_cap = 0;
+        HM_CUDA_CHECK(cudaMalloc(&ctx->d_buf, dneed + dneed / 2));
+        ctx->d_cap = dneed + dneed / 2;
+    }
+    if (ctx->h_cap < hneed) {
+        if (ctx->h_buf) cudaFreeHost(ctx->h_buf);
+        ctx->h_buf = nullptr; ctx->h_cap = 0;
+        HM_CUDA_CHECK(cudaMallocHost(&ctx->h_buf, hneed + hneed / 2));
+        ctx->h_cap = hneed + hneed / 2;
+    }
+    return HM_OK;
+}
+
+static void copy_rows(uint8_t* dst, const uint8_t* src, int64_t n, int64_t stride)
+{
+    if (stride == HM_DESC_BYTES) {
+        memcpy(dst, src, (size_t)n * HM_DESC_BYTES);
+    } else {
+        for (int64_t i = 0; i < n; ++i) memcpy(dst + i * HM_DESC_BYTES, src + i * stride, HM_DESC_BYTES);
+    }
+}
+
+HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq, int64_t q_stride,
+                         const uint8_t* train_host, int64_t nt, int64_t t_stride, unsigned flags,
+                         const uint16_t* ratio_lut_host, double dist_threshold, int variant, int32_t* out_q_host,
+                         int32_t* out_t_host, int32_t* out_d_host, int32_t* out_count_host)
+{
+    if (!ctx || nq < 0 || nt < 0 || !out_count_host || (nq > 0 && (!query_host || !out_q_host || !out_t_host || !out_d_host)) ||
+        (nt > 0 && !train_host) || q_stride < HM_DESC_BYTES || t_stride < HM_DESC_BYTES) {
+        set_error("hm_match_host: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    *out_count_host = 0;
+    if (nq == 0 || nt == 0) return HM_OK;          // cv2: no matches when either side is empty
+    const size_t qb = align_up((size_t)nq * HM_DESC_BYTES, 1024), tb = align_up((size_t)nt * HM_DESC_BYTES, 1024);
+    const size_t rb = align_up((size_t)nq * 12 + 16, 1024);      // [count | pad][q][t][d]
+    const size_t wsb = align_up(hm_workspace_bytes(nq, nt, 1, variant), 1024);
+    int rc = ctx_reserve(ctx, qb + tb + rb + wsb, qb + tb + rb);
+    if (rc != HM_OK) return rc;
+    uint8_t *dq = ctx->d_buf, *dt = dq + qb, *dr = dt + tb, *dw = dr + rb;
+    uint8_t *hq = ctx->h_buf, *ht = hq + qb, *hr = ht + tb;
+    copy_rows(hq, query_host, nq, q_stride);
+    copy_rows(ht, train_host, nt, t_stride);
+    // query and train staging are adjacent: one H2D covers both
+    HM_CUDA_CHECK(cudaMemcpyAsync(dq, hq, qb + (size_t)nt * HM_DESC_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    int32_t* d_count = reinterpret_cast<int32_t*>(dr);
+    int32_t* d_q = reinterpret_cast<int32_t*>(dr + 16);
+    int32_t* d_t = d_q + nq;
+    int32_t* d_d = d_t + nq;
+    rc = hm_match_fused(dq, nq, HM_DESC_BYTES, 0, dt, nt, HM_DESC_BYTES, 0, 1, flags, ratio_lut_host, dist_threshold, d_q,
+                        d_t, d_d, d_count, nullptr, variant, dw, wsb, ctx->stream);
+    if (rc != HM_OK) return rc;
+    HM_CUDA_CHECK(cudaMemcpyAsync(hr, dr, (size_t)nq * 12 + 16, cudaMemcpyDeviceToHost, ctx->stream));
+    HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    const int32_t n = *reinterpret_cast<int32_t*>(hr);
+    const int32_t* h_q = reinterpret_cast<int32_t*>(hr + 16);
+    memcpy(out_q_host, h_q, (size_t)n * 4);
+    memcpy(out_t_host, h_q + nq, (size_t)n * 4);
+    memcpy(out_d_host, h_q + 2 * nq, (size_t)n * 4);
+    *out_count_host = n;
+    return HM_OK;
+}
+
 }  // extern "C"

@@ -147,20 +147,6 @@ __device__ __forceinline__ void tmem_ld_fence4(uint32_t (&a)[32], uint32_t (&b)[
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(a), HM_R32(b), HM_R32(c), HM_R32(d) : : "memory");
 }
 
-__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32])
-{
-    // wait for the asynchronous register writes of tcgen05.ld; the "+r" operands pin the
-    // ordering of every later use of r[] after this point
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
-                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]),
-                   "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]),
-                   "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]),
-                   "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
-                 :
-                 : "memory");
-}
-
 // 32 consecutive train columns of one query row.  Fast path: 3-input-max trees give the maximum
 // of each group of 8 columns and of the whole chunk; one compare + branch per chunk against the
 // running second best decides whether anything can change the top-2.  Only then are the groups

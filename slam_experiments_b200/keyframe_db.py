@@ -154,6 +154,4 @@ class ShardedKeyframeDatabase:
         if kk == 0:
             return tuple(() for _ in range(nq))
         qi = np.repeat(np.arange(nq, dtype=np.int32), kk)
-        flat = _build_dmatches(qi.tolist(), local.reshape(-1).tolist(),
-                               dist.reshape(-1).astype(np.float32).tolist(), img.reshape(-1).tolist())
-        return tuple(tuple(flat[i * kk:(i + 1) * kk]) for i in range(nq))
+        return _build_dmatches(qi, local.reshape(-1), dist.reshape(-1), img.reshape(-1), rows=kk)
