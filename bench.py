@@ -206,7 +206,8 @@ def run_b200(args):
     kf_lo, kf_hi, row_lo, row_hi = sx.shard_ranges(sizes, world)[rank]
     local_kfs = [train[i * KF_ROWS:(i + 1) * KF_ROWS] for i in range(kf_lo, kf_hi)]
     db = sx.ShardedKeyframeDatabase(sizes, local_kfs, rank=rank, world_size=world,
-                                    group=None if world == 1 else dist.group.WORLD, device=dev, variant=args.variant)
+                                    group=None if world == 1 else dist.group.WORLD, device=dev, variant=args.variant,
+                                    exchange=args.exchange)
     del local_kfs
     q_dev = torch.from_numpy(query).to(dev)
     nt_local = row_hi - row_lo
@@ -306,12 +307,14 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "u8", "data": "synthetic", "config": dict(c4_config(world), variant=variant_used,
+        "dtype": "u8", "data": "synthetic", "config": dict(c4_config(world), variant=variant_used, exchange=db.exchange_mode,
                                                          db_format="train shard resident as +/-1 int8 (expanded once at add())"),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * 32, "d2h_bytes_per_step": NQ * 16,
                 "ms_per_step": e2e_s * 1e3, "api": "ShardedKeyframeDatabase.knnMatch(query_numpy, 2) -> DMatch tuples",
                 "arrays_out_ms_per_step": e2e_arr_s * 1e3},
+        # per step: prepare(query) + k-NN + split merge, plus (N>1) the fused exchange kernel, or the merge
+        # kernel after NCCL's all-gather
         "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
         "roofline": roofline,
         "verified_vs_oracle": verified,
@@ -346,6 +349,7 @@ def main():
     ap.add_argument("--variant", default="auto", choices=["auto", "popc", "i8"])
     ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
     ap.add_argument("--n", type=int, default=65536, help="c3: N x N")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"])
     ap.add_argument("--no-verify", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

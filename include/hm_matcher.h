@@ -124,6 +124,21 @@ HM_API int hm_knn2_prepared(const void* query_prepared, int64_t nq,
  * Merges per-shard results after the all-gather of the sharded keyframe database. */
 HM_API int hm_merge_top2(const uint64_t* keys, int groups, int64_t rows, uint64_t* out_keys, void* stream);
 
+/* Fused exchange + merge for the sharded keyframe database (one launch per rank, no NCCL call):
+ * every rank pushes its [rows][2] local keys straight into slot `rank` of every peer's symmetric
+ * buffer with NVLink peer stores, publishes a per-CTA epoch flag (release, system scope), waits for
+ * the matching flags of all peers (acquire), and merges the `world` slots into out_keys.
+ *  peer_buffers_host[world]  host array of DEVICE pointers to the same symmetric allocation on each
+ *                            rank (peer-mapped, e.g. torch.distributed._symmetric_memory buffer_ptrs);
+ *                            each at least hm_exchange_bytes(max_rows, world) bytes, zero-initialised
+ *  epoch                     strictly increasing per call (1, 2, 3, ...), identical on all ranks
+ * All ranks must launch the call; the kernels wait on one another across GPUs (never run two ranks
+ * on one GPU).  A peer that never arrives trips a bounded spin and the kernel traps. */
+HM_API size_t hm_exchange_bytes(int64_t max_rows, int world);
+HM_API int hm_exchange_merge(const uint64_t* local_keys, int64_t rows, int world, int rank,
+                             void* const* peer_buffers_host, int64_t max_rows, uint32_t epoch,
+                             uint64_t* out_keys, void* stream);
+
 /* Ratio test / mutual check / reference distance filter + ordered compaction, per problem.
  *  fwd_keys[batch][nq][2]  from hm_knn2*(query, train)
  *  bwd_keys[batch][nt][2]  from hm_knn2*(train, query) (roles swapped); only read with HM_FLAG_MUTUAL

@@ -31,7 +31,7 @@ PREPARED_ROW_BYTES = 256
 EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
     "hm_knn2", "hm_knn2_batched", "hm_prepared_bytes", "hm_prepare", "hm_knn2_prepared",
-    "hm_merge_top2", "hm_filter_matches", "hm_match_fused",
+    "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host",
 )
 
@@ -68,6 +68,10 @@ def _declare(L):
     L.hm_knn2_prepared.argtypes = [vp, i64, vp, i64, u64, vp, vp, sz, vp]
     L.hm_merge_top2.restype = ci
     L.hm_merge_top2.argtypes = [vp, ci, i64, vp, vp]
+    L.hm_exchange_bytes.restype = sz
+    L.hm_exchange_bytes.argtypes = [i64, ci]
+    L.hm_exchange_merge.restype = ci
+    L.hm_exchange_merge.argtypes = [vp, i64, ci, ci, vp, i64, c.c_uint32, vp, vp]
     L.hm_filter_matches.restype = ci
     L.hm_filter_matches.argtypes = [vp, i64, vp, i64, ci, cu, vp, c.c_double, vp, vp, vp, vp, vp]
     L.hm_match_fused.restype = ci
@@ -237,6 +241,24 @@ def merge_top2(keys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.
         out = torch.empty((rows, 2), dtype=torch.int64, device=dev)
     with torch.cuda.device(dev):
         check(lib().hm_merge_top2(keys.data_ptr(), g, rows, out.data_ptr(), _stream_ptr(dev)), "hm_merge_top2")
+    return out
+
+
+def exchange_bytes(max_rows: int, world: int) -> int:
+    return int(lib().hm_exchange_bytes(max_rows, world))
+
+
+def exchange_merge(local_keys: torch.Tensor, world: int, rank: int, peer_ptrs, max_rows: int, epoch: int,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``hm_exchange_merge``: push local keys to every peer's symmetric buffer, flag, wait, merge."""
+    dev = local_keys.device
+    rows = local_keys.shape[0]
+    if out is None:
+        out = torch.empty((rows, 2), dtype=torch.int64, device=dev)
+    arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    with torch.cuda.device(dev):
+        check(lib().hm_exchange_merge(local_keys.data_ptr(), rows, world, rank, arr, max_rows, epoch, out.data_ptr(),
+                                      _stream_ptr(dev)), "hm_exchange_merge")
     return out
 
 

@@ -275,6 +275,28 @@ HM_API int hm_merge_top2(const uint64_t* keys, int groups, int64_t rows, uint64_
                              reinterpret_cast<unsigned long long*>(out_keys), static_cast<cudaStream_t>(stream));
 }
 
+HM_API size_t hm_exchange_bytes(int64_t max_rows, int world)
+{
+    if (max_rows <= 0 || world < 1 || world > kMaxWorld) return 0;
+    return exchange_bytes(max_rows, world);
+}
+
+HM_API int hm_exchange_merge(const uint64_t* local_keys, int64_t rows, int world, int rank,
+                             void* const* peer_buffers_host, int64_t max_rows, uint32_t epoch, uint64_t* out_keys,
+                             void* stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (!local_keys || !out_keys || !peer_buffers_host) {
+        set_error("hm_exchange_merge: null pointer");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    return launch_exchange_merge(reinterpret_cast<const unsigned long long*>(local_keys), rows, world, rank,
+                                 peer_buffers_host, max_rows, epoch, reinterpret_cast<unsigned long long*>(out_keys),
+                                 static_cast<cudaStream_t>(stream));
+}
+
 static int build_filter_args(unsigned flags, const uint16_t* ratio_lut_host, double dist_threshold, RatioLut* lut,
                              int* thr_ceil)
 {

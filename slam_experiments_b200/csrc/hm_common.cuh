@@ -79,6 +79,13 @@ int launch_i8_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_
 int launch_merge_top2(const unsigned long long* keys, int groups, long long rows, unsigned long long* out,
                       cudaStream_t stream);
 
+constexpr int kMaxWorld = 8;
+constexpr int kExchangeThreads = 256;
+size_t exchange_bytes(long long max_rows, int world);
+int launch_exchange_merge(const unsigned long long* local_keys, long long rows, int world, int rank,
+                          void* const* peers, long long max_rows, unsigned epoch, unsigned long long* out,
+                          cudaStream_t stream);
+
 struct RatioLut {
     unsigned short v[257];
 };

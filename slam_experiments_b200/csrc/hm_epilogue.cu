@@ -32,6 +32,87 @@ __global__ void __launch_bounds__(256) hm_merge_top2_kernel(const unsigned long 
     *reinterpret_cast<ulonglong2*>(out + r * 2) = make_ulonglong2(k1, k2);
 }
 
+// ---- fused cross-GPU exchange + merge ------------------------------------------------------------
+// Symmetric buffer layout (identical on every rank):
+//   [2 parities][world slots][max_rows][2] u64 keys | [world][max_ctas] u32 epoch flags
+struct ExchangeParams {
+    const unsigned long long* local;
+    unsigned long long* out;
+    long long rows, max_rows;
+    int world, rank;
+    unsigned epoch;
+    unsigned char* peer[kMaxWorld];
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__host__ __device__ inline long long exchange_max_ctas(long long max_rows) { return (max_rows + kExchangeThreads - 1) / kExchangeThreads; }
+__host__ __device__ inline size_t exchange_keys_bytes(long long max_rows, int world)
+{
+    return (size_t)2 * world * max_rows * 2 * sizeof(unsigned long long);
+}
+
+__global__ void __launch_bounds__(kExchangeThreads) hm_exchange_merge_kernel(const ExchangeParams P)
+{
+    const long long r = (long long)blockIdx.x * kExchangeThreads + threadIdx.x;
+    const int parity = P.epoch & 1;
+    const size_t slot_keys = (size_t)P.max_rows * 2;
+    const size_t keys_bytes = exchange_keys_bytes(P.max_rows, P.world);
+    const long long max_ctas = exchange_max_ctas(P.max_rows);
+
+    // 1. push this rank's candidates into slot `rank` of every rank's buffer (peer stores over NVLink)
+    ulonglong2 mine = make_ulonglong2(kNoMatch, kNoMatch);
+    if (r < P.rows) {
+        mine = *reinterpret_cast<const ulonglong2*>(P.local + r * 2);
+        for (int p = 0; p < P.world; ++p) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.peer[p]) +
+                                      ((size_t)parity * P.world + P.rank) * slot_keys + r * 2;
+            *reinterpret_cast<ulonglong2*>(dst) = mine;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    // 2. publish: flag[rank][cta] = epoch on every peer; 3. wait for every peer's flag for this CTA
+    if (threadIdx.x < P.world) {
+        const int p = threadIdx.x;
+        unsigned* flag = reinterpret_cast<unsigned*>(P.peer[p] + keys_bytes) + (size_t)P.rank * max_ctas + blockIdx.x;
+        st_release_sys(flag, P.epoch);
+        const unsigned* want = reinterpret_cast<const unsigned*>(P.peer[P.rank] + keys_bytes) + (size_t)p * max_ctas + blockIdx.x;
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(want) - P.epoch) < 0) {
+            if (++spins > (1u << 27)) __trap();          // a missing peer must not hang the GPU
+        }
+    }
+    __syncthreads();
+    // 4. merge the `world` slots of this rank's own buffer
+    if (r < P.rows) {
+        unsigned long long k1 = kNoMatch, k2 = kNoMatch;
+        const unsigned long long* base = reinterpret_cast<const unsigned long long*>(P.peer[P.rank]) +
+                                         (size_t)parity * P.world * slot_keys + r * 2;
+        for (int g = 0; g < P.world; ++g) {
+            ulonglong2 k = mine;
+            if (g != P.rank) {   // written by a peer GPU: bypass L1
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n"
+                             : "=l"(k.x), "=l"(k.y)
+                             : "l"(base + (size_t)g * slot_keys)
+                             : "memory");
+            }
+            top2_insert(k1, k2, k.x);
+            top2_insert(k1, k2, k.y);
+        }
+        *reinterpret_cast<ulonglong2*>(P.out + r * 2) = make_ulonglong2(k1, k2);
+    }
+}
+
 constexpr int kFilterThreads = 1024;
 
 struct FilterParams {
@@ -134,6 +215,36 @@ int launch_merge_top2(const unsigned long long* keys, int groups, long long rows
     const int threads = 256;
     const long long blocks = ceil_div(rows, threads);
     hm_merge_top2_kernel<<<(unsigned)blocks, threads, 0, stream>>>(keys, groups, rows, out);
+    HM_CUDA_CHECK(cudaGetLastError());
+    return HM_OK;
+}
+
+size_t exchange_bytes(long long max_rows, int world)
+{
+    return exchange_keys_bytes(max_rows, world) + (size_t)world * exchange_max_ctas(max_rows) * sizeof(unsigned) + 256;
+}
+
+int launch_exchange_merge(const unsigned long long* local_keys, long long rows, int world, int rank,
+                          void* const* peers, long long max_rows, unsigned epoch, unsigned long long* out,
+                          cudaStream_t stream)
+{
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || rows > max_rows || rows <= 0 || epoch == 0) {
+        set_error("hm_exchange_merge: bad arguments (world %d rank %d rows %lld max_rows %lld epoch %u)", world, rank,
+                  rows, max_rows, epoch);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    ExchangeParams P{};
+    P.local = local_keys; P.out = out; P.rows = rows; P.max_rows = max_rows; P.world = world; P.rank = rank; P.epoch = epoch;
+    for (int i = 0; i < world; ++i) {
+        if (!peers[i]) {
+            set_error("hm_exchange_merge: null peer buffer %d", i);
+            return HM_ERR_INVALID_ARGUMENT;
+        }
+        P.peer[i] = static_cast<unsigned char*>(peers[i]);
+    }
+    // the grid must cover max_rows (not just rows) so that every rank runs the same CTAs and flags
+    const long long ctas = exchange_max_ctas(max_rows);
+    hm_exchange_merge_kernel<<<(unsigned)ctas, kExchangeThreads, 0, stream>>>(P);
     HM_CUDA_CHECK(cudaGetLastError());
     return HM_OK;
 }

@@ -85,6 +85,38 @@ class NativeOps:
     def merge(self, gathered: torch.Tensor) -> torch.Tensor:
         return nat.merge_top2(gathered)
 
+    # ---- fused exchange: peer stores into symmetric memory + flags + merge, one launch, no NCCL call ----
+    def setup_exchange(self, group, world: int, rank: int, max_rows: int = 4096) -> str:
+        """Allocate and rendezvous the symmetric buffer of ``hm_exchange_merge``.  Returns the mode in
+        use: ``"fused"`` or ``"nccl"`` (when symmetric memory cannot be set up on this system)."""
+        self._xch = None
+        try:
+            import torch.distributed as dist
+            import torch.distributed._symmetric_memory as symm
+            nbytes = nat.exchange_bytes(max_rows, world)
+            with torch.cuda.device(self.device):
+                buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
+                buf.zero_()
+                torch.cuda.synchronize(self.device)
+                handle = symm.rendezvous(buf, group if group is not None else dist.group.WORLD)
+                ptrs = [int(p) for p in handle.buffer_ptrs]
+                dist.barrier(group)                      # every rank's flags are zero before the first epoch
+            if len(ptrs) != world or any(p == 0 for p in ptrs):
+                raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
+            self._xch = {"buf": buf, "handle": handle, "ptrs": ptrs, "max_rows": max_rows, "epoch": 0,
+                         "world": world, "rank": rank}
+            return "fused"
+        except Exception as e:  # symmetric memory unavailable: the NCCL all-gather path still works
+            self._xch_error = f"{type(e).__name__}: {e}"
+            return "nccl"
+
+    def gather_merge(self, local: torch.Tensor, group) -> torch.Tensor:
+        x = getattr(self, "_xch", None)
+        if x is not None and 0 < local.shape[0] <= x["max_rows"]:
+            x["epoch"] += 1
+            return nat.exchange_merge(local.contiguous(), x["world"], x["rank"], x["ptrs"], x["max_rows"], x["epoch"])
+        return self.merge(self.all_gather(local, group))
+
     def to_host(self, keys: torch.Tensor) -> np.ndarray:
         with torch.cuda.device(self.device):
             return self._staging.to_host("keys", keys)
@@ -99,7 +131,8 @@ class ShardedKeyframeDatabase:
     """
 
     def __init__(self, sizes: Sequence[int], local_keyframes: Sequence[np.ndarray], *, rank: int = 0,
-                 world_size: int = 1, group=None, ops=None, device=None, variant: str = "auto"):
+                 world_size: int = 1, group=None, ops=None, device=None, variant: str = "auto",
+                 exchange: str = "auto", max_query_rows: int = 4096):
         self.sizes = np.asarray(sizes, dtype=np.int64)
         self.starts = np.concatenate([[0], np.cumsum(self.sizes)])
         self.rank, self.world_size, self.group = rank, world_size, group
@@ -118,6 +151,12 @@ class ShardedKeyframeDatabase:
         cat = (np.concatenate([np.asarray(a) for a in local_keyframes], axis=0)
                if len(local_keyframes) else np.empty((0, nat.DESC_BYTES), np.uint8))
         self.shard = self.ops.make_shard(self.ops.upload(cat))
+        # exchange step: "fused" = hm_exchange_merge over symmetric memory, "nccl" = all-gather + merge
+        self.exchange_mode = "none" if world_size == 1 else "nccl"
+        if world_size > 1 and exchange in ("auto", "fused") and hasattr(self.ops, "setup_exchange"):
+            self.exchange_mode = self.ops.setup_exchange(group, world_size, rank, max_query_rows)
+            if exchange == "fused" and self.exchange_mode != "fused":
+                raise nat.NativeError(f"fused exchange unavailable: {getattr(self.ops, '_xch_error', '?')}")
 
     # ---- device-level API ---------------------------------------------------------------------
     def knn2_keys_device(self, query_dev: torch.Tensor) -> torch.Tensor:
@@ -125,6 +164,8 @@ class ShardedKeyframeDatabase:
         local = self.ops.local_knn2(query_dev, self.shard, self.row_lo)
         if self.world_size == 1:
             return local
+        if self.exchange_mode == "fused":
+            return self.ops.gather_merge(local, self.group)
         gathered = self.ops.all_gather(local, self.group)
         return self.ops.merge(gathered)
 
