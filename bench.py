@@ -50,7 +50,11 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU while the timed region runs.
+
+    NVML (nvidia_ml_py) is polled every few milliseconds from a thread so that even a 40 ms timed
+    region gets several samples; falls back to `nvidia-smi -lms 50` when NVML is unavailable.
+    """
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -60,8 +64,32 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [x.strip() for x in vis.split(",") if x.strip()]
+            if self.gpu < len(ids) and ids[self.gpu].isdigit():
+                return int(ids[self.gpu])
+        return self.gpu
 
     def start(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self._nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -71,11 +99,37 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self._nvml
+        bits = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                if get_reasons:
+                    mask = int(get_reasons(self._h))
+                    for name, bit in bits.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+            except Exception:
+                break
+            self._stop.wait(0.004)
+
     def _read(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self._nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1)
+            sm = self.samples
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_min_mhz": float(min(sm)) if sm else None,
+                    "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         time.sleep(0.15)
@@ -99,7 +153,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
 def make_c4(n_keyframes=N_KEYFRAMES, rows=KF_ROWS, nq=NQ):
@@ -315,7 +369,7 @@ def run_b200(args):
                 "arrays_out_ms_per_step": e2e_arr_s * 1e3},
         # per step: prepare(query) + k-NN + split merge, plus (N>1) the fused exchange kernel, or the merge
         # kernel after NCCL's all-gather
-        "gpu_launches": args.steps * (3 + (1 if world > 1 else 0)),
+        "gpu_launches": args.steps * (3 if world == 1 or db.exchange_mode == "fused" else 4),
         "roofline": roofline,
         "verified_vs_oracle": verified,
     }

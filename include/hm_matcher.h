@@ -113,11 +113,21 @@ HM_API int hm_knn2_batched(const uint8_t* query, int64_t nq, int64_t q_stride, i
 HM_API size_t hm_prepared_bytes(int64_t n);
 /* expand n packed descriptors into `prepared` (hm_prepared_bytes(n) bytes) */
 HM_API int hm_prepare(const uint8_t* bits, int64_t n, int64_t stride, void* prepared, void* stream);
+/* scratch bytes hm_knn2_prepared / hm_knn2_prepared_partials need (no operand expansion inside) */
+HM_API size_t hm_prepared_workspace_bytes(int64_t nq, int64_t nt);
 /* k-NN over operands prepared once (train side of a keyframe database stays resident) */
 HM_API int hm_knn2_prepared(const void* query_prepared, int64_t nq,
                             const void* train_prepared, int64_t nt,
                             uint64_t train_base, uint64_t* out_keys,
                             void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same k-NN, but the per-train-split partial keys are left unmerged in the workspace:
+ * *out_partials -> [*out_groups][nq][2] (valid until the workspace is reused on the stream).
+ * Feed them to hm_exchange_merge (or hm_merge_top2) to save one launch on the sharded path. */
+HM_API int hm_knn2_prepared_partials(const void* query_prepared, int64_t nq,
+                                     const void* train_prepared, int64_t nt, uint64_t train_base,
+                                     void* workspace, size_t workspace_bytes, void* stream,
+                                     const uint64_t** out_partials, int* out_groups);
 
 /* ---- epilogues ------------------------------------------------------------------------ */
 /* keys[groups][rows][2] -> out_keys[rows][2]: the 2 smallest of the 2*groups candidates per row.
@@ -132,10 +142,12 @@ HM_API int hm_merge_top2(const uint64_t* keys, int groups, int64_t rows, uint64_
  *                            rank (peer-mapped, e.g. torch.distributed._symmetric_memory buffer_ptrs);
  *                            each at least hm_exchange_bytes(max_rows, world) bytes, zero-initialised
  *  epoch                     strictly increasing per call (1, 2, 3, ...), identical on all ranks
+ *  local_keys[local_groups][rows][2]  this rank's candidates; local_groups > 1 folds the merge of the
+ *                            k-NN kernel's train splits (hm_knn2_prepared_partials) into the same launch
  * All ranks must launch the call; the kernels wait on one another across GPUs (never run two ranks
  * on one GPU).  A peer that never arrives trips a bounded spin and the kernel traps. */
 HM_API size_t hm_exchange_bytes(int64_t max_rows, int world);
-HM_API int hm_exchange_merge(const uint64_t* local_keys, int64_t rows, int world, int rank,
+HM_API int hm_exchange_merge(const uint64_t* local_keys, int local_groups, int64_t rows, int world, int rank,
                              void* const* peer_buffers_host, int64_t max_rows, uint32_t epoch,
                              uint64_t* out_keys, void* stream);
 

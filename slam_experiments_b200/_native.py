@@ -30,7 +30,7 @@ PREPARED_ROW_BYTES = 256
 # every symbol include/hm_matcher.h declares (tests check the library exports all of them)
 EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
-    "hm_knn2", "hm_knn2_batched", "hm_prepared_bytes", "hm_prepare", "hm_knn2_prepared",
+    "hm_knn2", "hm_knn2_batched", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials",
     "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host",
 )
@@ -62,6 +62,8 @@ def _declare(L):
     L.hm_knn2_batched.argtypes = [vp, i64, i64, i64, vp, i64, i64, i64, ci, vp, ci, vp, sz, vp]
     L.hm_prepared_bytes.restype = sz
     L.hm_prepared_bytes.argtypes = [i64]
+    L.hm_prepared_workspace_bytes.restype = sz
+    L.hm_prepared_workspace_bytes.argtypes = [i64, i64]
     L.hm_prepare.restype = ci
     L.hm_prepare.argtypes = [vp, i64, i64, vp, vp]
     L.hm_knn2_prepared.restype = ci
@@ -71,7 +73,9 @@ def _declare(L):
     L.hm_exchange_bytes.restype = sz
     L.hm_exchange_bytes.argtypes = [i64, ci]
     L.hm_exchange_merge.restype = ci
-    L.hm_exchange_merge.argtypes = [vp, i64, ci, ci, vp, i64, c.c_uint32, vp, vp]
+    L.hm_exchange_merge.argtypes = [vp, ci, i64, ci, ci, vp, i64, c.c_uint32, vp, vp]
+    L.hm_knn2_prepared_partials.restype = ci
+    L.hm_knn2_prepared_partials.argtypes = [vp, i64, vp, i64, u64, vp, sz, vp, c.POINTER(vp), c.POINTER(ci)]
     L.hm_filter_matches.restype = ci
     L.hm_filter_matches.argtypes = [vp, i64, vp, i64, ci, cu, vp, c.c_double, vp, vp, vp, vp, vp]
     L.hm_match_fused.restype = ci
@@ -224,7 +228,7 @@ def knn2_keys_prepared(query_prepared: torch.Tensor, nq: int, train_prepared: to
         out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
     L = lib()
     with torch.cuda.device(dev):
-        wsb = L.hm_workspace_bytes(nq, nt, 1, VARIANT_I8)
+        wsb = L.hm_prepared_workspace_bytes(nq, nt)
         ws = workspace(wsb, dev)
         check(L.hm_knn2_prepared(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
                                  out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "hm_knn2_prepared")
@@ -248,18 +252,40 @@ def exchange_bytes(max_rows: int, world: int) -> int:
     return int(lib().hm_exchange_bytes(max_rows, world))
 
 
-def exchange_merge(local_keys: torch.Tensor, world: int, rank: int, peer_ptrs, max_rows: int, epoch: int,
-                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``hm_exchange_merge``: push local keys to every peer's symmetric buffer, flag, wait, merge."""
-    dev = local_keys.device
-    rows = local_keys.shape[0]
+def exchange_merge(local_keys, world: int, rank: int, peer_ptrs, max_rows: int, epoch: int,
+                   out: Optional[torch.Tensor] = None, *, rows: Optional[int] = None, groups: int = 1,
+                   device=None) -> torch.Tensor:
+    """``hm_exchange_merge``: push local keys to every peer's symmetric buffer, flag, wait, merge.
+
+    ``local_keys`` is a ``[rows, 2]`` tensor, or a raw device pointer to ``[groups][rows][2]`` partials
+    (from :func:`knn2_partials_prepared`) together with ``rows`` / ``groups`` / ``device``."""
+    if isinstance(local_keys, torch.Tensor):
+        dev, rows, ptr = local_keys.device, local_keys.shape[0], local_keys.data_ptr()
+    else:
+        dev, ptr = device, int(local_keys)
     if out is None:
         out = torch.empty((rows, 2), dtype=torch.int64, device=dev)
-    arr = (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    arr = peer_ptrs if isinstance(peer_ptrs, ctypes.Array) else (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
     with torch.cuda.device(dev):
-        check(lib().hm_exchange_merge(local_keys.data_ptr(), rows, world, rank, arr, max_rows, epoch, out.data_ptr(),
+        check(lib().hm_exchange_merge(ptr, groups, rows, world, rank, arr, max_rows, epoch, out.data_ptr(),
                                       _stream_ptr(dev)), "hm_exchange_merge")
     return out
+
+
+def knn2_partials_prepared(query_prepared: torch.Tensor, nq: int, train_prepared: torch.Tensor, nt: int,
+                           train_base: int = 0):
+    """``hm_knn2_prepared_partials``: returns ``(device_ptr, groups)`` of the unmerged per-split keys,
+    valid until the cached workspace is reused on this stream."""
+    dev = query_prepared.device
+    L = lib()
+    parts, groups = ctypes.c_void_p(), ctypes.c_int(0)
+    with torch.cuda.device(dev):
+        wsb = L.hm_prepared_workspace_bytes(nq, nt)
+        ws = workspace(wsb, dev)
+        check(L.hm_knn2_prepared_partials(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
+                                          ws.data_ptr(), ws.numel(), _stream_ptr(dev), ctypes.byref(parts),
+                                          ctypes.byref(groups)), "hm_knn2_prepared_partials")
+    return parts.value, groups.value
 
 
 def ratio_lut(ratio: float) -> np.ndarray:

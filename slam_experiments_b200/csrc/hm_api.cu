@@ -219,6 +219,15 @@ HM_API int hm_knn2_batched(const uint8_t* query, int64_t nq, int64_t q_stride, i
                          static_cast<cudaStream_t>(stream));
 }
 
+HM_API size_t hm_prepared_workspace_bytes(int64_t nq, int64_t nt)
+{
+    DeviceInfo di;
+    int sm = 148;
+    if (device_info(&di) == HM_OK) sm = di.sm_count;
+    if (nq <= 0 || nt <= 0) return 256;
+    return align_up(i8_workspace_bytes(nq, nt, 1, sm, false));
+}
+
 HM_API size_t hm_prepared_bytes(int64_t n) { return n > 0 ? prepared_bytes(n) : 0; }
 
 HM_API int hm_prepare(const uint8_t* bits, int64_t n, int64_t stride, void* prepared, void* stream)
@@ -262,6 +271,24 @@ HM_API int hm_knn2_prepared(const void* query_prepared, int64_t nq, const void* 
                                    di.sm_count, st);
 }
 
+HM_API int hm_knn2_prepared_partials(const void* query_prepared, int64_t nq, const void* train_prepared, int64_t nt,
+                                     uint64_t train_base, void* workspace, size_t workspace_bytes, void* stream,
+                                     const uint64_t** out_partials, int* out_groups)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (nq <= 0 || nt <= 0 || !out_partials || !out_groups || !query_prepared || !train_prepared) {
+        set_error("hm_knn2_prepared_partials: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    const unsigned long long* parts = nullptr;
+    rc = launch_i8_knn2_prepared(query_prepared, nq, train_prepared, nt, 1, train_base, nullptr, workspace,
+                                 workspace_bytes, di.sm_count, static_cast<cudaStream_t>(stream), &parts, out_groups);
+    *out_partials = reinterpret_cast<const uint64_t*>(parts);
+    return rc;
+}
+
 HM_API int hm_merge_top2(const uint64_t* keys, int groups, int64_t rows, uint64_t* out_keys, void* stream)
 {
     DeviceInfo di;
@@ -281,7 +308,7 @@ HM_API size_t hm_exchange_bytes(int64_t max_rows, int world)
     return exchange_bytes(max_rows, world);
 }
 
-HM_API int hm_exchange_merge(const uint64_t* local_keys, int64_t rows, int world, int rank,
+HM_API int hm_exchange_merge(const uint64_t* local_keys, int local_groups, int64_t rows, int world, int rank,
                              void* const* peer_buffers_host, int64_t max_rows, uint32_t epoch, uint64_t* out_keys,
                              void* stream)
 {
@@ -292,7 +319,7 @@ HM_API int hm_exchange_merge(const uint64_t* local_keys, int64_t rows, int world
         set_error("hm_exchange_merge: null pointer");
         return HM_ERR_INVALID_ARGUMENT;
     }
-    return launch_exchange_merge(reinterpret_cast<const unsigned long long*>(local_keys), rows, world, rank,
+    return launch_exchange_merge(reinterpret_cast<const unsigned long long*>(local_keys), local_groups, rows, world, rank,
                                  peer_buffers_host, max_rows, epoch, reinterpret_cast<unsigned long long*>(out_keys),
                                  static_cast<cudaStream_t>(stream));
 }

@@ -68,9 +68,12 @@ size_t popc_workspace_bytes(long long nq, long long nt, int batch, int sm_count)
 size_t prepared_bytes(long long n);
 int launch_prepare(const uint8_t* bits, long long n, long long stride, long long batch_stride, int batch,
                    void* prepared, cudaStream_t stream);
+// out == nullptr: leave the per-split partials in the workspace and report them through
+// out_partials / out_groups instead of merging
 int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
                             unsigned long long train_base, unsigned long long* out, void* ws,
-                            size_t ws_bytes, int sm_count, cudaStream_t stream);
+                            size_t ws_bytes, int sm_count, cudaStream_t stream,
+                            const unsigned long long** out_partials = nullptr, int* out_groups = nullptr);
 size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare);
 int launch_i8_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count,
                    cudaStream_t stream);
@@ -82,7 +85,7 @@ int launch_merge_top2(const unsigned long long* keys, int groups, long long rows
 constexpr int kMaxWorld = 8;
 constexpr int kExchangeThreads = 256;
 size_t exchange_bytes(long long max_rows, int world);
-int launch_exchange_merge(const unsigned long long* local_keys, long long rows, int world, int rank,
+int launch_exchange_merge(const unsigned long long* local_keys, int local_groups, long long rows, int world, int rank,
                           void* const* peers, long long max_rows, unsigned epoch, unsigned long long* out,
                           cudaStream_t stream);
 

@@ -36,7 +36,8 @@ __global__ void __launch_bounds__(256) hm_merge_top2_kernel(const unsigned long 
 // Symmetric buffer layout (identical on every rank):
 //   [2 parities][world slots][max_rows][2] u64 keys | [world][max_ctas] u32 epoch flags
 struct ExchangeParams {
-    const unsigned long long* local;
+    const unsigned long long* local;   // [local_groups][rows][2]
+    int local_groups;
     unsigned long long* out;
     long long rows, max_rows;
     int world, rank;
@@ -72,7 +73,11 @@ __global__ void __launch_bounds__(kExchangeThreads) hm_exchange_merge_kernel(con
     // 1. push this rank's candidates into slot `rank` of every rank's buffer (peer stores over NVLink)
     ulonglong2 mine = make_ulonglong2(kNoMatch, kNoMatch);
     if (r < P.rows) {
-        mine = *reinterpret_cast<const ulonglong2*>(P.local + r * 2);
+        for (int g = 0; g < P.local_groups; ++g) {   // fold the k-NN kernel's train splits
+            const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(P.local + ((long long)g * P.rows + r) * 2);
+            top2_insert(mine.x, mine.y, k.x);
+            top2_insert(mine.x, mine.y, k.y);
+        }
         for (int p = 0; p < P.world; ++p) {
             unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.peer[p]) +
                                       ((size_t)parity * P.world + P.rank) * slot_keys + r * 2;
@@ -224,17 +229,18 @@ size_t exchange_bytes(long long max_rows, int world)
     return exchange_keys_bytes(max_rows, world) + (size_t)world * exchange_max_ctas(max_rows) * sizeof(unsigned) + 256;
 }
 
-int launch_exchange_merge(const unsigned long long* local_keys, long long rows, int world, int rank,
+int launch_exchange_merge(const unsigned long long* local_keys, int local_groups, long long rows, int world, int rank,
                           void* const* peers, long long max_rows, unsigned epoch, unsigned long long* out,
                           cudaStream_t stream)
 {
-    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || rows > max_rows || rows <= 0 || epoch == 0) {
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || rows > max_rows || rows <= 0 || epoch == 0 ||
+        local_groups < 1) {
         set_error("hm_exchange_merge: bad arguments (world %d rank %d rows %lld max_rows %lld epoch %u)", world, rank,
                   rows, max_rows, epoch);
         return HM_ERR_INVALID_ARGUMENT;
     }
     ExchangeParams P{};
-    P.local = local_keys; P.out = out; P.rows = rows; P.max_rows = max_rows; P.world = world; P.rank = rank; P.epoch = epoch;
+    P.local = local_keys; P.local_groups = local_groups; P.out = out; P.rows = rows; P.max_rows = max_rows; P.world = world; P.rank = rank; P.epoch = epoch;
     for (int i = 0; i < world; ++i) {
         if (!peers[i]) {
             set_error("hm_exchange_merge: null peer buffer %d", i);

@@ -471,7 +471,7 @@ int launch_prepare(const uint8_t* bits, long long n, long long stride, long long
 static size_t i8_partials_bytes(long long nq, long long nt, int batch, int sm_count)
 {
     const I8Plan pl = plan_i8(nq, nt, batch, sm_count);
-    return pl.splits > 1 ? (size_t)pl.splits * batch * nq * 2 * sizeof(unsigned long long) : 0;
+    return (size_t)pl.splits * batch * nq * 2 * sizeof(unsigned long long);   // also when splits == 1 (partials mode)
 }
 
 size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare)
@@ -484,7 +484,8 @@ size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, b
 
 int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
                             unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
-                            int sm_count, cudaStream_t stream)
+                            int sm_count, cudaStream_t stream, const unsigned long long** out_partials,
+                            int* out_groups)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -496,7 +497,8 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
         set_error("train set too large for 32-bit trainIdx");
         return HM_ERR_UNSUPPORTED;
     }
-    const size_t need = 256 + i8_partials_bytes(nq, nt, batch, sm_count);
+    const bool keep_partials = out == nullptr;
+    const size_t need = 256 + (keep_partials ? (size_t)pl.splits * batch * nq * 16 : i8_partials_bytes(nq, nt, batch, sm_count));
     if (!ws || ws_bytes < need) {
         set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
         return HM_ERR_WORKSPACE;
@@ -519,7 +521,7 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
     }
     const long long rows = nq * batch;
     unsigned long long* partials = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + 256);
-    if (pl.splits > 1) {
+    if (pl.splits > 1 || keep_partials) {
         P.out = partials;
         P.out_split_stride = rows * 2;
     } else {
@@ -566,6 +568,11 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
             }
             fclose(f);
         }
+    }
+    if (keep_partials) {
+        if (out_partials) *out_partials = partials;
+        if (out_groups) *out_groups = pl.splits;
+        return HM_OK;
     }
     if (pl.splits > 1) return launch_merge_top2(partials, pl.splits, rows, out, stream);
     return HM_OK;

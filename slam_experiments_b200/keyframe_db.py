@@ -103,12 +103,26 @@ class NativeOps:
                 dist.barrier(group)                      # every rank's flags are zero before the first epoch
             if len(ptrs) != world or any(p == 0 for p in ptrs):
                 raise RuntimeError("symmetric memory rendezvous returned no peer pointers")
-            self._xch = {"buf": buf, "handle": handle, "ptrs": ptrs, "max_rows": max_rows, "epoch": 0,
-                         "world": world, "rank": rank}
+            import ctypes
+            self._xch = {"buf": buf, "handle": handle, "ptrs": (ctypes.c_void_p * world)(*ptrs), "max_rows": max_rows,
+                         "epoch": 0, "world": world, "rank": rank}
             return "fused"
         except Exception as e:  # symmetric memory unavailable: the NCCL all-gather path still works
             self._xch_error = f"{type(e).__name__}: {e}"
             return "nccl"
+
+    def local_knn2_exchange(self, query: torch.Tensor, shard, train_base: int, group) -> torch.Tensor:
+        """Local k-NN + exchange with the split merge folded into the exchange kernel (2 launches + the
+        query expansion per step instead of 4)."""
+        x = getattr(self, "_xch", None)
+        nq = query.shape[0]
+        if x is None or shard["prepared"] is None or not (0 < nq <= x["max_rows"]):
+            return self.gather_merge(self.local_knn2(query, shard, train_base), group)
+        qprep = nat.prepare(query)
+        ptr, groups = nat.knn2_partials_prepared(qprep, nq, shard["prepared"], shard["nt"], train_base)
+        x["epoch"] += 1
+        return nat.exchange_merge(ptr, x["world"], x["rank"], x["ptrs"], x["max_rows"], x["epoch"], rows=nq,
+                                  groups=groups, device=self.device)
 
     def gather_merge(self, local: torch.Tensor, group) -> torch.Tensor:
         x = getattr(self, "_xch", None)
@@ -161,11 +175,11 @@ class ShardedKeyframeDatabase:
     # ---- device-level API ---------------------------------------------------------------------
     def knn2_keys_device(self, query_dev: torch.Tensor) -> torch.Tensor:
         """Global top-2 keys ``[Nq, 2]`` (identical on every rank)."""
+        if self.world_size > 1 and self.exchange_mode == "fused":
+            return self.ops.local_knn2_exchange(query_dev, self.shard, self.row_lo, self.group)
         local = self.ops.local_knn2(query_dev, self.shard, self.row_lo)
         if self.world_size == 1:
             return local
-        if self.exchange_mode == "fused":
-            return self.ops.gather_merge(local, self.group)
         gathered = self.ops.all_gather(local, self.group)
         return self.ops.merge(gathered)
 
