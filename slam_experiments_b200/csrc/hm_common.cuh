@@ -57,6 +57,50 @@ __device__ __forceinline__ void top2_insert(unsigned long long& k1, unsigned lon
     k2 = hi < k2 ? hi : k2;
 }
 
+// ---- in-kernel merge of train splits ("last CTA done" pattern) ---------------------------------------
+// Every CTA of a k-NN kernel writes its partial keys to partials[split][row][2]; the CTA that arrives last
+// on the per-row-block counter folds all splits and writes the final keys, so no merge kernel is launched.
+// min over keys is order independent, so the result does not depend on which CTA is last.
+__device__ __forceinline__ bool last_cta_arrives(unsigned* counter, unsigned expected, int* smem_flag)
+{
+    __threadfence();                       // this thread's partial keys are visible device-wide
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned old = atomicAdd(counter, 1u);
+        const int last = old == expected - 1;
+        if (last) *counter = 0;            // ready for the next launch on this workspace
+        *smem_flag = last;
+    }
+    __syncthreads();
+    const bool last = *smem_flag != 0;
+    if (last) __threadfence();
+    return last;
+}
+
+// top-2 of one row over `groups` partial results (L2-coherent loads, 8 in flight)
+__device__ __forceinline__ void fold_partials(const unsigned long long* keys, int groups, long long group_stride,
+                                              long long r, unsigned long long& k1, unsigned long long& k2)
+{
+    int g = 0;
+    for (; g + 8 <= groups; g += 8) {
+        ulonglong2 k[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) k[j] = __ldcg(reinterpret_cast<const ulonglong2*>(keys + (long long)(g + j) * group_stride + r * 2));
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            top2_insert(k1, k2, k[j].x);
+            top2_insert(k1, k2, k[j].y);
+        }
+    }
+    for (; g < groups; ++g) {
+        const ulonglong2 k = __ldcg(reinterpret_cast<const ulonglong2*>(keys + (long long)g * group_stride + r * 2));
+        top2_insert(k1, k2, k.x);
+        top2_insert(k1, k2, k.y);
+    }
+}
+
+inline size_t counters_bytes(long long row_blocks) { return (size_t)((row_blocks * 4 + 255) / 256 * 256); }
+
 // ---- launchers implemented in the .cu files -------------------------------------------
 // (a) POPC variant.  partial == nullptr -> writes final keys to out.
 int popc_splits(const KnnProblem& p, int sm_count);

@@ -24,11 +24,7 @@ __global__ void __launch_bounds__(256) hm_merge_top2_kernel(const unsigned long 
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= rows) return;
     unsigned long long k1 = kNoMatch, k2 = kNoMatch;
-    for (int g = 0; g < groups; ++g) {
-        const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(keys + ((long long)g * rows + r) * 2);
-        top2_insert(k1, k2, k.x);
-        top2_insert(k1, k2, k.y);
-    }
+    fold_partials(keys, groups, rows * 2, r, k1, k2);
     *reinterpret_cast<ulonglong2*>(out + r * 2) = make_ulonglong2(k1, k2);
 }
 
@@ -73,11 +69,7 @@ __global__ void __launch_bounds__(kExchangeThreads) hm_exchange_merge_kernel(con
     // 1. push this rank's candidates into slot `rank` of every rank's buffer (peer stores over NVLink)
     ulonglong2 mine = make_ulonglong2(kNoMatch, kNoMatch);
     if (r < P.rows) {
-        for (int g = 0; g < P.local_groups; ++g) {   // fold the k-NN kernel's train splits
-            const ulonglong2 k = *reinterpret_cast<const ulonglong2*>(P.local + ((long long)g * P.rows + r) * 2);
-            top2_insert(mine.x, mine.y, k.x);
-            top2_insert(mine.x, mine.y, k.y);
-        }
+        fold_partials(P.local, P.local_groups, P.rows * 2, r, mine.x, mine.y);   // fold the k-NN kernel's train splits
         for (int p = 0; p < P.world; ++p) {
             unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.peer[p]) +
                                       ((size_t)parity * P.world + P.rank) * slot_keys + r * 2;
@@ -217,7 +209,7 @@ int launch_merge_top2(const unsigned long long* keys, int groups, long long rows
                       cudaStream_t stream)
 {
     if (rows <= 0) return HM_OK;
-    const int threads = 256;
+    const int threads = 64;      // few rows: spread them over many SMs
     const long long blocks = ceil_div(rows, threads);
     hm_merge_top2_kernel<<<(unsigned)blocks, threads, 0, stream>>>(keys, groups, rows, out);
     HM_CUDA_CHECK(cudaGetLastError());

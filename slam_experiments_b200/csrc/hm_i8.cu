@@ -111,6 +111,9 @@ struct I8Params {
     unsigned long long* out;         // [split][batch][nq][2]
     long long out_split_stride;      // keys
     int* error_flag;
+    unsigned long long* final_out;   // [batch][nq][2]: written by the last CTA of each query block when merging in-kernel
+    unsigned* counters;              // [batch][qblocks] arrival counters (zeroed by the launcher), null = no in-kernel merge
+    int splits;
     long long q_blocks_valid;        // 256-row blocks present in qprep (CTAs beyond it are cluster padding)
     long long* trace;                // development aid (HM_I8_TRACE): per-tile clock64 stamps of CTA 0, else null
 };
@@ -367,6 +370,18 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
+    // ---- in-kernel merge of the train splits: the last CTA of this query block folds all partials ----
+    if (P.counters) {
+        int* flag = reinterpret_cast<int*>(tmem_base_slot + 1);
+        if (last_cta_arrives(&P.counters[(long long)b * gridDim.x + qb], (unsigned)P.splits, flag)) {
+            const long long row = (long long)qb * kBlockM + threadIdx.x;
+            if (threadIdx.x < kBlockM && row < P.nq) {
+                unsigned long long k1 = kNoMatch, k2 = kNoMatch;
+                fold_partials(P.out, P.splits, P.out_split_stride, (long long)b * P.nq + row, k1, k2);
+                *reinterpret_cast<ulonglong2*>(P.final_out + ((long long)b * P.nq + row) * 2) = make_ulonglong2(k1, k2);
+            }
+        }
+    }
 }
 
 struct I8Plan {
@@ -467,7 +482,7 @@ int launch_prepare(const uint8_t* bits, long long n, long long stride, long long
     return HM_OK;
 }
 
-// workspace layout: [error flag 256 B][partials][prepared q][prepared t]
+// workspace layout: [256 B][arrival counters][partials][prepared q][prepared t]
 static size_t i8_partials_bytes(long long nq, long long nt, int batch, int sm_count)
 {
     const I8Plan pl = plan_i8(nq, nt, batch, sm_count);
@@ -476,7 +491,7 @@ static size_t i8_partials_bytes(long long nq, long long nt, int batch, int sm_co
 
 size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare)
 {
-    size_t b = 256 + i8_partials_bytes(nq, nt, batch, sm_count);
+    size_t b = 256 + counters_bytes(plan_i8(nq, nt, batch, sm_count).qblocks * batch) + i8_partials_bytes(nq, nt, batch, sm_count);
     b = (b + 1023) & ~(size_t)1023;
     if (with_prepare) b += (prepared_bytes(nq) + prepared_bytes(nt)) * batch;
     return b;
@@ -498,7 +513,8 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
         return HM_ERR_UNSUPPORTED;
     }
     const bool keep_partials = out == nullptr;
-    const size_t need = 256 + (keep_partials ? (size_t)pl.splits * batch * nq * 16 : i8_partials_bytes(nq, nt, batch, sm_count));
+    const size_t cbytes = counters_bytes(pl.qblocks * batch);
+    const size_t need = 256 + cbytes + i8_partials_bytes(nq, nt, batch, sm_count);
     if (!ws || ws_bytes < need) {
         set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
         return HM_ERR_WORKSPACE;
@@ -520,10 +536,17 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
         HM_CUDA_CHECK(cudaMemset(P.trace, 0, sizeof(long long) * kTraceTiles * kTraceSlots));
     }
     const long long rows = nq * batch;
-    unsigned long long* partials = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + 256);
+    unsigned* counters = reinterpret_cast<unsigned*>(static_cast<uint8_t*>(ws) + 256);
+    unsigned long long* partials = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + 256 + cbytes);
+    P.splits = pl.splits;
     if (pl.splits > 1 || keep_partials) {
         P.out = partials;
         P.out_split_stride = rows * 2;
+        if (!keep_partials) {              // merge in-kernel: the last CTA per query block writes `out`
+            P.counters = counters;
+            P.final_out = out;
+            HM_CUDA_CHECK(cudaMemsetAsync(counters, 0, cbytes, stream));
+        }
     } else {
         P.out = out;
         P.out_split_stride = 0;
@@ -574,7 +597,6 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
         if (out_groups) *out_groups = pl.splits;
         return HM_OK;
     }
-    if (pl.splits > 1) return launch_merge_top2(partials, pl.splits, rows, out, stream);
     return HM_OK;
 }
 

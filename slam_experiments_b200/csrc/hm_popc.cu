@@ -31,6 +31,8 @@ struct PopcParams {
     int splits;
     unsigned long long* out;         // [split][batch][nq][2] (split stride 0 when splits == 1)
     long long out_split_stride;      // in keys
+    unsigned long long* final_out;   // [batch][nq][2], written by the last CTA of each query tile (splits > 1)
+    unsigned* counters;              // [batch][query tiles] arrival counters, zeroed by the launcher
 };
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
@@ -147,6 +149,20 @@ __global__ void __launch_bounds__(kThreads) hm_popc_knn2_kernel(const PopcParams
             *reinterpret_cast<ulonglong2*>(out + qrow[u] * 2) = k;
         }
     }
+    // ---- in-kernel merge of the train splits: the last CTA of this query tile folds all partials ----
+    if (P.counters) {
+        __shared__ int last_flag;
+        if (last_cta_arrives(&P.counters[(long long)b * gridDim.x + blockIdx.x], (unsigned)P.splits, &last_flag)) {
+#pragma unroll
+            for (int u = 0; u < QPT; ++u) {
+                if (qrow[u] < P.p.nq) {
+                    unsigned long long k1 = kNoMatch, k2 = kNoMatch;
+                    fold_partials(P.out, P.splits, P.out_split_stride, (long long)b * P.p.nq + qrow[u], k1, k2);
+                    *reinterpret_cast<ulonglong2*>(P.final_out + ((long long)b * P.p.nq + qrow[u]) * 2) = make_ulonglong2(k1, k2);
+                }
+            }
+        }
+    }
 }
 
 int queries_per_thread(long long nq, int batch, int sm_count)
@@ -185,8 +201,12 @@ size_t popc_workspace_bytes(long long nq, long long nt, int batch, int sm_count)
 {
     KnnProblem p{};
     p.nq = nq; p.nt = nt; p.batch = batch;
-    const int s = popc_splits(p, sm_count);
-    return s > 1 ? (size_t)s * batch * nq * 2 * sizeof(unsigned long long) : 0;
+    int qpt, s;
+    long long chunk;
+    plan(p, sm_count, &qpt, &s, &chunk);
+    if (s <= 1) return 0;
+    const long long qtiles = ceil_div(nq, (long long)kThreads * qpt);
+    return counters_bytes(qtiles * batch) + (size_t)s * batch * nq * 2 * sizeof(unsigned long long);
 }
 
 int launch_popc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count,
@@ -204,19 +224,23 @@ int launch_popc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, siz
     P.chunk = chunk;
     P.splits = splits;
     const long long rows = p.nq * p.batch;
+    const long long qtiles = ceil_div(p.nq, (long long)kThreads * qpt);
     if (splits > 1) {
-        const size_t need = (size_t)splits * rows * 2 * sizeof(unsigned long long);
+        const size_t cbytes = counters_bytes(qtiles * p.batch);
+        const size_t need = cbytes + (size_t)splits * rows * 2 * sizeof(unsigned long long);
         if (!ws || ws_bytes < need) {
             set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
             return HM_ERR_WORKSPACE;
         }
-        P.out = static_cast<unsigned long long*>(ws);
+        P.counters = static_cast<unsigned*>(ws);
+        P.final_out = out;
+        P.out = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(ws) + cbytes);
         P.out_split_stride = rows * 2;
+        HM_CUDA_CHECK(cudaMemsetAsync(P.counters, 0, cbytes, stream));
     } else {
         P.out = out;
         P.out_split_stride = 0;
     }
-    const long long qtiles = ceil_div(p.nq, (long long)kThreads * qpt);
     if (qtiles > 0x7FFFFFFFll || p.batch > 65535) {
         set_error("grid too large");
         return HM_ERR_UNSUPPORTED;
@@ -229,7 +253,6 @@ int launch_popc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, siz
         hm_popc_knn2_kernel<1><<<grid, kThreads, 0, stream>>>(P);
     profile_mark(false, stream);
     HM_CUDA_CHECK(cudaGetLastError());
-    if (splits > 1) return launch_merge_top2(P.out, splits, rows, out, stream);
     return HM_OK;
 }
 
