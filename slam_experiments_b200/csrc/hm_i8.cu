@@ -48,8 +48,7 @@ constexpr int kABytes = kMBlocks * kRowBlockBytes;   // 64 KB
 constexpr int kBStageBytes = kRowBlockBytes;         // 32 KB
 constexpr int kTmemCols = 512;               // 2 buffers x 2 query blocks x 128 columns
 constexpr int kEpilogueWarps = 4 * kMBlocks; // one per 32 query rows
-constexpr int kIssuerWarp1 = 2 + kEpilogueWarps;     // second MMA issuer (query block 1)
-constexpr int kThreads = 32 * (kIssuerWarp1 + 1);    // warp 0 producer, warp 1 / warp 10 MMA issuers, warps 2..9 epilogue
+constexpr int kThreads = 32 * (2 + kEpilogueWarps);  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
 constexpr int kSmemBytes = 1024 + kABytes + kStages * kBStageBytes + 256;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
@@ -222,7 +221,7 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], kMBlocks * cs);   // one (multicast) commit per MMA issuer of the cluster
+            ptx::mbar_init(&empty_bar[i], cs);           // one (multicast) commit per CTA of the cluster
         }
         ptx::mbar_init(a_full_bar, 1);
         for (int i = 0; i < 2 * kMBlocks; ++i) {
@@ -263,59 +262,71 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
                 else        ptx::bulk_g2s(dst, src, piece, &full_bar[stage]);
             }
         }
-    } else if (warp == 1 || warp == kIssuerWarp1) {
-        // ===== MMA issuers: one warp per 128-row query block =====
-        // tcgen05.mma issue blocks while the tensor-core queue is full, so a single issuer exposes its
-        // barrier round trips (~150 cycles each) between groups of MMAs; two issuers alternate, each
-        // hiding its waits behind the other's 8 MMAs (trace: profiles/r01c_trace_*).
-        const int m = warp == 1 ? 0 : 1;
-        constexpr uint32_t idesc = ptx::make_i8_idesc(kRowBlock, kBlockN);
-        const uint32_t a_addr = ptx::smem_u32(smem_a) + m * kRowBlockBytes;
-        const uint32_t b_addr = ptx::smem_u32(smem_b);
-        if (has_a) bounded_wait(a_full_bar, 0, P.error_flag);
-        bool ready = false;                               // barriers of tile i already observed complete
-        for (int i = 0; i < my_tiles; ++i) {
-            const int stage = i % kStages;
-            const uint32_t use = i / kStages;
-            const int unit = (i & 1) * kMBlocks + m;
-            const uint32_t unit_use = i >> 1;
-            if (lane == 0 && m == 0) trace_mark(P, i, 7);           // issuer 0: loop top
-            if (!ready) {
-                bounded_wait(&full_bar[stage], use & 1, P.error_flag);
-                bounded_wait(&tmem_empty_bar[unit], (unit_use & 1) ^ 1, P.error_flag);
-            }
-            if (lane == 0) trace_mark(P, i, m == 0 ? 1 : 6);        // operands landed, accumulator unit free
-            ptx::tc_fence_after();
-            const bool leader = ptx::elect_one();
-            const uint32_t b_stage = b_addr + stage * kBStageBytes;
-            if (leader) {
+    } else if (warp == 1) {
+        // ===== MMA issuer: ONE thread runs the whole issue loop =====
+        // tcgen05.mma issue blocks while the tensor-core queue is full, so every barrier round trip
+        // (~100-150 cycles) taken between two groups of MMAs is a bubble in the tensor pipe.  The
+        // barriers of the NEXT group are therefore probed (mbarrier.test_wait, non-blocking) in the
+        // middle of the current group, while its MMAs execute; the blocking wait is only the fallback.
+        // (Two issuer warps were tried: they fall into lockstep on the shared barriers and their gaps
+        // coincide -- trace in profiles/r01c_trace_i8_64k.txt.)
+        if (ptx::elect_one()) {
+            constexpr uint32_t idesc = ptx::make_i8_idesc(kRowBlock, kBlockN);
+            const uint32_t a_addr = ptx::smem_u32(smem_a);
+            const uint32_t b_addr = ptx::smem_u32(smem_b);
+            if (has_a) bounded_wait(a_full_bar, 0, P.error_flag);
+            bool ready0 = false;                          // full[stage] and empty[unit 0] of tile i observed
+            for (int i = 0; i < my_tiles; ++i) {
+                const int stage = i % kStages;
+                const uint32_t use = i / kStages;
+                const int unit0 = (i & 1) * kMBlocks;
+                const uint32_t unit_par = ((uint32_t)(i >> 1) & 1) ^ 1;
+                const uint32_t b_stage = b_addr + stage * kBStageBytes;
+                trace_mark(P, i, 7);                       // loop top
+                if (!ready0) {
+                    bounded_wait(&full_bar[stage], use & 1, P.error_flag);
+                    bounded_wait(&tmem_empty_bar[unit0], unit_par, P.error_flag);
+                }
+                trace_mark(P, i, 1);                       // operands landed, unit 0 free
+                ptx::tc_fence_after();
+                // ---- query block 0 ----
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    ptx::mma_i8_ss(tmem_base + unit * kBlockN, ptx::make_kmajor_sw128_desc(a_addr + k * 32),
+                    ptx::mma_i8_ss(tmem_base + unit0 * kBlockN, ptx::make_kmajor_sw128_desc(a_addr + k * 32),
                                    ptx::make_kmajor_sw128_desc(b_stage + k * 32), idesc, k != 0);
-            }
-            // Probe the next tile's barriers while the tensor core works through the MMAs above, so the
-            // ~100-cycle barrier round trips are not exposed between tiles (issue blocks on a full queue).
-            ready = false;
-            if (i + 1 < my_tiles) {
-                const int nstage = (i + 1) % kStages;
-                const int nunit = ((i + 1) & 1) * kMBlocks + m;
-                ready = ptx::mbar_test_wait(&full_bar[nstage], ((i + 1) / kStages) & 1) &&
-                        ptx::mbar_test_wait(&tmem_empty_bar[nunit], ((((i + 1) >> 1)) & 1) ^ 1);
-                ready = __all_sync(0xFFFFFFFFu, ready);
-            }
-            if (leader) {
+                const bool ready1 = ptx::mbar_test_wait(&tmem_empty_bar[unit0 + 1], unit_par);
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
-                    ptx::mma_i8_ss(tmem_base + unit * kBlockN, ptx::make_kmajor_sw128_desc(a_addr + kSlabBytes + k * 32),
+                    ptx::mma_i8_ss(tmem_base + unit0 * kBlockN, ptx::make_kmajor_sw128_desc(a_addr + kSlabBytes + k * 32),
                                    ptx::make_kmajor_sw128_desc(b_stage + kSlabBytes + k * 32), idesc, 1);
-                ptx::tc_commit(&tmem_full_bar[unit]);     // this query block's accumulator is ready
-                // smem stage reusable (by every producer of the cluster) once both issuers' MMAs retire
+                ptx::tc_commit(&tmem_full_bar[unit0]);     // query block 0's accumulator is ready
+                // ---- query block 1 ----
+                if (!ready1) bounded_wait(&tmem_empty_bar[unit0 + 1], unit_par, P.error_flag);
+                trace_mark(P, i, 6);                       // unit 1 free
+                ptx::tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::mma_i8_ss(tmem_base + (unit0 + 1) * kBlockN,
+                                   ptx::make_kmajor_sw128_desc(a_addr + kRowBlockBytes + k * 32),
+                                   ptx::make_kmajor_sw128_desc(b_stage + k * 32), idesc, k != 0);
+                ready0 = false;
+                if (i + 1 < my_tiles) {
+                    const int n = i + 1;
+                    ready0 = ptx::mbar_test_wait(&full_bar[n % kStages], (n / kStages) & 1) &&
+                             ptx::mbar_test_wait(&tmem_empty_bar[(n & 1) * kMBlocks], (((uint32_t)(n >> 1)) & 1) ^ 1);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    ptx::mma_i8_ss(tmem_base + (unit0 + 1) * kBlockN,
+                                   ptx::make_kmajor_sw128_desc(a_addr + kRowBlockBytes + kSlabBytes + k * 32),
+                                   ptx::make_kmajor_sw128_desc(b_stage + kSlabBytes + k * 32), idesc, 1);
+                ptx::tc_commit(&tmem_full_bar[unit0 + 1]);
+                // smem stage reusable (by every producer of the cluster) once these MMAs retire
                 if (cs > 1) ptx::tc_commit_multicast(&empty_bar[stage], cmask);
                 else        ptx::tc_commit(&empty_bar[stage]);
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
         // ===== epilogue: TMEM -> registers, running top-2 per query row =====
         const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
@@ -435,7 +446,9 @@ I8Plan plan_i8(long long nq, long long nt, int batch, int sm_count)
 {
     I8Plan pl{};
     const long long qb = ceil_div(nq, kBlockM);
-    pl.cluster = 1;
+    // pairs of query blocks share every train tile through multicast: half the L2 reads, +1.7 % on the
+    // power-capped C4 workload (6297 vs 6189 Gpairs/s); clusters of 4 lose SMs to GPC packing (6003)
+    pl.cluster = qb >= 2 ? 2 : 1;
     if (cluster_override()) pl.cluster = cluster_override();
     pl.qblocks = ceil_div(qb, pl.cluster) * pl.cluster;
     sm_count = resident_ctas(pl.cluster, sm_count);
@@ -581,7 +594,7 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
         HM_CUDA_CHECK(cudaMemcpy(host, P.trace, sizeof(host), cudaMemcpyDeviceToHost));
         cudaFree(P.trace);
         if (FILE* f = fopen(trace_path, "w")) {
-            fprintf(f, "# tile producer_issue issuer0_ready (unused) epi2_full epi2_scanned epi9_full issuer1_unit_free issuer0_loop_top (cycles since first stamp); tiles/CTA=%d splits=%d cluster=%d\n",
+            fprintf(f, "# tile producer_issue issuer_ready (unused) epi2_full epi2_scanned epi9_full issuer_unit1_free issuer_loop_top (cycles since first stamp); tiles/CTA=%d splits=%d cluster=%d\n",
                     pl.tiles_per_split, pl.splits, pl.cluster);
             long long t0 = host[0];
             for (int i = 0; i < kTraceTiles; ++i) {
