@@ -151,6 +151,16 @@ HM_API int hm_exchange_merge(const uint64_t* local_keys, int local_groups, int64
                              void* const* peer_buffers_host, int64_t max_rows, uint32_t epoch,
                              uint64_t* out_keys, void* stream);
 
+/* k-NN over prepared operands with the exchange folded into the same launch: the CTA that finishes a
+ * query block last merges the train splits, pushes the block's keys to every peer, waits for the peers'
+ * blocks and writes the globally merged top-2 -- compute + collective in ONE kernel per rank.
+ * Same buffer / epoch contract as hm_exchange_merge (the two may be mixed on one buffer). */
+HM_API int hm_knn2_prepared_exchange(const void* query_prepared, int64_t nq,
+                                     const void* train_prepared, int64_t nt, uint64_t train_base,
+                                     int world, int rank, void* const* peer_buffers_host, int64_t max_rows,
+                                     uint32_t epoch, uint64_t* out_keys,
+                                     void* workspace, size_t workspace_bytes, void* stream);
+
 /* Ratio test / mutual check / reference distance filter + ordered compaction, per problem.
  *  fwd_keys[batch][nq][2]  from hm_knn2*(query, train)
  *  bwd_keys[batch][nt][2]  from hm_knn2*(train, query) (roles swapped); only read with HM_FLAG_MUTUAL

@@ -30,7 +30,7 @@ PREPARED_ROW_BYTES = 256
 # every symbol include/hm_matcher.h declares (tests check the library exports all of them)
 EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
-    "hm_knn2", "hm_knn2_batched", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials",
+    "hm_knn2", "hm_knn2_batched", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials", "hm_knn2_prepared_exchange",
     "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host",
 )
@@ -74,6 +74,8 @@ def _declare(L):
     L.hm_exchange_bytes.argtypes = [i64, ci]
     L.hm_exchange_merge.restype = ci
     L.hm_exchange_merge.argtypes = [vp, ci, i64, ci, ci, vp, i64, c.c_uint32, vp, vp]
+    L.hm_knn2_prepared_exchange.restype = ci
+    L.hm_knn2_prepared_exchange.argtypes = [vp, i64, vp, i64, u64, ci, ci, vp, i64, c.c_uint32, vp, vp, sz, vp]
     L.hm_knn2_prepared_partials.restype = ci
     L.hm_knn2_prepared_partials.argtypes = [vp, i64, vp, i64, u64, vp, sz, vp, c.POINTER(vp), c.POINTER(ci)]
     L.hm_filter_matches.restype = ci
@@ -269,6 +271,24 @@ def exchange_merge(local_keys, world: int, rank: int, peer_ptrs, max_rows: int, 
     with torch.cuda.device(dev):
         check(lib().hm_exchange_merge(ptr, groups, rows, world, rank, arr, max_rows, epoch, out.data_ptr(),
                                       _stream_ptr(dev)), "hm_exchange_merge")
+    return out
+
+
+def knn2_prepared_exchange(query_prepared: torch.Tensor, nq: int, train_prepared: torch.Tensor, nt: int,
+                           train_base: int, world: int, rank: int, peer_ptrs, max_rows: int, epoch: int,
+                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``hm_knn2_prepared_exchange``: local k-NN + cross-GPU exchange + merge in one launch."""
+    dev = query_prepared.device
+    if out is None:
+        out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
+    arr = peer_ptrs if isinstance(peer_ptrs, ctypes.Array) else (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    L = lib()
+    with torch.cuda.device(dev):
+        wsb = L.hm_prepared_workspace_bytes(nq, nt)
+        ws = workspace(wsb, dev)
+        check(L.hm_knn2_prepared_exchange(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
+                                          world, rank, arr, max_rows, epoch, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          _stream_ptr(dev)), "hm_knn2_prepared_exchange")
     return out
 
 

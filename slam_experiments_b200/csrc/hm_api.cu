@@ -289,6 +289,25 @@ HM_API int hm_knn2_prepared_partials(const void* query_prepared, int64_t nq, con
     return rc;
 }
 
+HM_API int hm_knn2_prepared_exchange(const void* query_prepared, int64_t nq, const void* train_prepared, int64_t nt,
+                                     uint64_t train_base, int world, int rank, void* const* peer_buffers_host,
+                                     int64_t max_rows, uint32_t epoch, uint64_t* out_keys, void* workspace,
+                                     size_t workspace_bytes, void* stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (nq <= 0 || nt <= 0 || !out_keys || !query_prepared || !train_prepared) {
+        set_error("hm_knn2_prepared_exchange: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    ExchangeArgs x;
+    if ((rc = fill_exchange_args(&x, world, rank, peer_buffers_host, max_rows, epoch, nq)) != HM_OK) return rc;
+    return launch_i8_knn2_prepared(query_prepared, nq, train_prepared, nt, 1, train_base,
+                                   reinterpret_cast<unsigned long long*>(out_keys), workspace, workspace_bytes,
+                                   di.sm_count, static_cast<cudaStream_t>(stream), nullptr, nullptr, &x);
+}
+
 HM_API int hm_merge_top2(const uint64_t* keys, int groups, int64_t rows, uint64_t* out_keys, void* stream)
 {
     DeviceInfo di;

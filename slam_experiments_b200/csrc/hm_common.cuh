@@ -99,6 +99,90 @@ __device__ __forceinline__ void fold_partials(const unsigned long long* keys, in
     }
 }
 
+// ---- cross-GPU exchange over symmetric memory (shared by hm_exchange_merge_kernel and the k-NN kernel's
+// last-CTA merge).  Symmetric buffer layout, identical on every rank:
+//   [2 parities][world slots][max_rows][2] u64 keys | [world][max_rows / 256] u32 epoch flags
+constexpr int kMaxWorld = 8;
+constexpr int kExchangeRows = 256;          // rows per flag (= rows per CTA of either kernel)
+
+struct ExchangeArgs {
+    unsigned char* peer[kMaxWorld];          // peer-mapped base of the symmetric buffer on every rank
+    int world, rank;
+    unsigned epoch;                          // 1, 2, 3, ... identical on all ranks
+    long long max_rows;
+};
+
+// row blocks with a flag each; even, because the k-NN kernel launches query blocks in cluster pairs
+__host__ __device__ inline long long exchange_blocks(long long max_rows)
+{
+    return (((max_rows + kExchangeRows - 1) / kExchangeRows) + 1) & ~1ll;
+}
+__host__ __device__ inline size_t exchange_keys_bytes(long long max_rows, int world)
+{
+    return (size_t)2 * world * max_rows * 2 * sizeof(unsigned long long);
+}
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Called by ALL threads of a CTA that owns row block `block` (rows [block*256, +256)); thread t < 256 passes
+// its row's local keys.  Pushes them into slot `rank` of every rank's buffer with peer stores, publishes
+// flag[rank][block] = epoch on every rank (release, system scope), waits for every rank's flag for this
+// block (acquire; bounded spin -> trap) and returns the merge of all slots for this thread's row.
+__device__ __forceinline__ ulonglong2 exchange_and_merge(const ExchangeArgs& X, long long r, bool has_row,
+                                                         ulonglong2 mine, long long block)
+{
+    const int parity = X.epoch & 1;
+    const size_t slot_keys = (size_t)X.max_rows * 2;
+    const size_t keys_bytes = exchange_keys_bytes(X.max_rows, X.world);
+    const long long nblocks = exchange_blocks(X.max_rows);
+    if (has_row) {
+        for (int p = 0; p < X.world; ++p) {
+            unsigned long long* dst = reinterpret_cast<unsigned long long*>(X.peer[p]) +
+                                      ((size_t)parity * X.world + X.rank) * slot_keys + r * 2;
+            *reinterpret_cast<ulonglong2*>(dst) = mine;
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < X.world) {
+        const int p = threadIdx.x;
+        unsigned* flag = reinterpret_cast<unsigned*>(X.peer[p] + keys_bytes) + (size_t)X.rank * nblocks + block;
+        st_release_sys(flag, X.epoch);
+        const unsigned* want = reinterpret_cast<const unsigned*>(X.peer[X.rank] + keys_bytes) + (size_t)p * nblocks + block;
+        unsigned spins = 0;
+        while ((int)(ld_acquire_sys(want) - X.epoch) < 0) {
+            if (++spins > (1u << 27)) __trap();          // a missing peer must not hang the GPU
+        }
+    }
+    __syncthreads();
+    unsigned long long k1 = kNoMatch, k2 = kNoMatch;
+    if (has_row) {
+        const unsigned long long* base = reinterpret_cast<const unsigned long long*>(X.peer[X.rank]) +
+                                         (size_t)parity * X.world * slot_keys + r * 2;
+        for (int g = 0; g < X.world; ++g) {
+            ulonglong2 k = mine;
+            if (g != X.rank) {   // written by a peer GPU: bypass L1
+                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n"
+                             : "=l"(k.x), "=l"(k.y)
+                             : "l"(base + (size_t)g * slot_keys)
+                             : "memory");
+            }
+            top2_insert(k1, k2, k.x);
+            top2_insert(k1, k2, k.y);
+        }
+    }
+    return make_ulonglong2(k1, k2);
+}
+
 inline size_t counters_bytes(long long row_blocks) { return (size_t)((row_blocks * 4 + 255) / 256 * 256); }
 
 // ---- launchers implemented in the .cu files -------------------------------------------
@@ -117,7 +201,10 @@ int launch_prepare(const uint8_t* bits, long long n, long long stride, long long
 int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
                             unsigned long long train_base, unsigned long long* out, void* ws,
                             size_t ws_bytes, int sm_count, cudaStream_t stream,
-                            const unsigned long long** out_partials = nullptr, int* out_groups = nullptr);
+                            const unsigned long long** out_partials = nullptr, int* out_groups = nullptr,
+                            const ExchangeArgs* exchange = nullptr);
+int fill_exchange_args(ExchangeArgs* x, int world, int rank, void* const* peers, long long max_rows, unsigned epoch,
+                       long long rows);
 size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare);
 int launch_i8_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count,
                    cudaStream_t stream);
@@ -126,8 +213,6 @@ int launch_i8_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_
 int launch_merge_top2(const unsigned long long* keys, int groups, long long rows, unsigned long long* out,
                       cudaStream_t stream);
 
-constexpr int kMaxWorld = 8;
-constexpr int kExchangeThreads = 256;
 size_t exchange_bytes(long long max_rows, int world);
 int launch_exchange_merge(const unsigned long long* local_keys, int local_groups, long long rows, int world, int rank,
                           void* const* peers, long long max_rows, unsigned epoch, unsigned long long* out,

@@ -11,6 +11,8 @@
 //    roles swapped.
 //  - distance filter: /root/reference/feature_matchers.py:41-43,
 //    keep d < max(2 * min_d, dist_threshold) (strict).
+#include <string.h>
+
 #include "hm_common.cuh"
 
 namespace hm {
@@ -28,86 +30,23 @@ __global__ void __launch_bounds__(256) hm_merge_top2_kernel(const unsigned long 
     *reinterpret_cast<ulonglong2*>(out + r * 2) = make_ulonglong2(k1, k2);
 }
 
-// ---- fused cross-GPU exchange + merge ------------------------------------------------------------
-// Symmetric buffer layout (identical on every rank):
-//   [2 parities][world slots][max_rows][2] u64 keys | [world][max_ctas] u32 epoch flags
+// ---- cross-GPU exchange + merge as a stand-alone launch (hm_exchange_merge) ---------------------------
 struct ExchangeParams {
     const unsigned long long* local;   // [local_groups][rows][2]
     int local_groups;
     unsigned long long* out;
-    long long rows, max_rows;
-    int world, rank;
-    unsigned epoch;
-    unsigned char* peer[kMaxWorld];
+    long long rows;
+    ExchangeArgs x;
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v)
+__global__ void __launch_bounds__(kExchangeRows) hm_exchange_merge_kernel(const ExchangeParams P)
 {
-    asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p)
-{
-    unsigned v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-__host__ __device__ inline long long exchange_max_ctas(long long max_rows) { return (max_rows + kExchangeThreads - 1) / kExchangeThreads; }
-__host__ __device__ inline size_t exchange_keys_bytes(long long max_rows, int world)
-{
-    return (size_t)2 * world * max_rows * 2 * sizeof(unsigned long long);
-}
-
-__global__ void __launch_bounds__(kExchangeThreads) hm_exchange_merge_kernel(const ExchangeParams P)
-{
-    const long long r = (long long)blockIdx.x * kExchangeThreads + threadIdx.x;
-    const int parity = P.epoch & 1;
-    const size_t slot_keys = (size_t)P.max_rows * 2;
-    const size_t keys_bytes = exchange_keys_bytes(P.max_rows, P.world);
-    const long long max_ctas = exchange_max_ctas(P.max_rows);
-
-    // 1. push this rank's candidates into slot `rank` of every rank's buffer (peer stores over NVLink)
+    const long long r = (long long)blockIdx.x * kExchangeRows + threadIdx.x;
+    const bool has_row = r < P.rows;
     ulonglong2 mine = make_ulonglong2(kNoMatch, kNoMatch);
-    if (r < P.rows) {
-        fold_partials(P.local, P.local_groups, P.rows * 2, r, mine.x, mine.y);   // fold the k-NN kernel's train splits
-        for (int p = 0; p < P.world; ++p) {
-            unsigned long long* dst = reinterpret_cast<unsigned long long*>(P.peer[p]) +
-                                      ((size_t)parity * P.world + P.rank) * slot_keys + r * 2;
-            *reinterpret_cast<ulonglong2*>(dst) = mine;
-        }
-    }
-    __threadfence_system();
-    __syncthreads();
-    // 2. publish: flag[rank][cta] = epoch on every peer; 3. wait for every peer's flag for this CTA
-    if (threadIdx.x < P.world) {
-        const int p = threadIdx.x;
-        unsigned* flag = reinterpret_cast<unsigned*>(P.peer[p] + keys_bytes) + (size_t)P.rank * max_ctas + blockIdx.x;
-        st_release_sys(flag, P.epoch);
-        const unsigned* want = reinterpret_cast<const unsigned*>(P.peer[P.rank] + keys_bytes) + (size_t)p * max_ctas + blockIdx.x;
-        unsigned spins = 0;
-        while ((int)(ld_acquire_sys(want) - P.epoch) < 0) {
-            if (++spins > (1u << 27)) __trap();          // a missing peer must not hang the GPU
-        }
-    }
-    __syncthreads();
-    // 4. merge the `world` slots of this rank's own buffer
-    if (r < P.rows) {
-        unsigned long long k1 = kNoMatch, k2 = kNoMatch;
-        const unsigned long long* base = reinterpret_cast<const unsigned long long*>(P.peer[P.rank]) +
-                                         (size_t)parity * P.world * slot_keys + r * 2;
-        for (int g = 0; g < P.world; ++g) {
-            ulonglong2 k = mine;
-            if (g != P.rank) {   // written by a peer GPU: bypass L1
-                asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];\n"
-                             : "=l"(k.x), "=l"(k.y)
-                             : "l"(base + (size_t)g * slot_keys)
-                             : "memory");
-            }
-            top2_insert(k1, k2, k.x);
-            top2_insert(k1, k2, k.y);
-        }
-        *reinterpret_cast<ulonglong2*>(P.out + r * 2) = make_ulonglong2(k1, k2);
-    }
+    if (has_row) fold_partials(P.local, P.local_groups, P.rows * 2, r, mine.x, mine.y);   // fold the train splits
+    const ulonglong2 k = exchange_and_merge(P.x, r, has_row, mine, blockIdx.x);
+    if (has_row) *reinterpret_cast<ulonglong2*>(P.out + r * 2) = k;
 }
 
 constexpr int kFilterThreads = 1024;
@@ -218,31 +157,43 @@ int launch_merge_top2(const unsigned long long* keys, int groups, long long rows
 
 size_t exchange_bytes(long long max_rows, int world)
 {
-    return exchange_keys_bytes(max_rows, world) + (size_t)world * exchange_max_ctas(max_rows) * sizeof(unsigned) + 256;
+    return exchange_keys_bytes(max_rows, world) + (size_t)world * exchange_blocks(max_rows) * sizeof(unsigned) + 256;
+}
+
+int fill_exchange_args(ExchangeArgs* x, int world, int rank, void* const* peers, long long max_rows, unsigned epoch,
+                       long long rows)
+{
+    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || rows > max_rows || rows <= 0 || epoch == 0 || !peers) {
+        set_error("exchange: bad arguments (world %d rank %d rows %lld max_rows %lld epoch %u)", world, rank, rows,
+                  max_rows, epoch);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    memset(x, 0, sizeof(*x));
+    x->world = world; x->rank = rank; x->epoch = epoch; x->max_rows = max_rows;
+    for (int i = 0; i < world; ++i) {
+        if (!peers[i]) {
+            set_error("exchange: null peer buffer %d", i);
+            return HM_ERR_INVALID_ARGUMENT;
+        }
+        x->peer[i] = static_cast<unsigned char*>(peers[i]);
+    }
+    return HM_OK;
 }
 
 int launch_exchange_merge(const unsigned long long* local_keys, int local_groups, long long rows, int world, int rank,
                           void* const* peers, long long max_rows, unsigned epoch, unsigned long long* out,
                           cudaStream_t stream)
 {
-    if (world < 1 || world > kMaxWorld || rank < 0 || rank >= world || rows > max_rows || rows <= 0 || epoch == 0 ||
-        local_groups < 1) {
-        set_error("hm_exchange_merge: bad arguments (world %d rank %d rows %lld max_rows %lld epoch %u)", world, rank,
-                  rows, max_rows, epoch);
+    ExchangeParams P{};
+    if (local_groups < 1) {
+        set_error("hm_exchange_merge: local_groups < 1");
         return HM_ERR_INVALID_ARGUMENT;
     }
-    ExchangeParams P{};
-    P.local = local_keys; P.local_groups = local_groups; P.out = out; P.rows = rows; P.max_rows = max_rows; P.world = world; P.rank = rank; P.epoch = epoch;
-    for (int i = 0; i < world; ++i) {
-        if (!peers[i]) {
-            set_error("hm_exchange_merge: null peer buffer %d", i);
-            return HM_ERR_INVALID_ARGUMENT;
-        }
-        P.peer[i] = static_cast<unsigned char*>(peers[i]);
-    }
-    // the grid must cover max_rows (not just rows) so that every rank runs the same CTAs and flags
-    const long long ctas = exchange_max_ctas(max_rows);
-    hm_exchange_merge_kernel<<<(unsigned)ctas, kExchangeThreads, 0, stream>>>(P);
+    int rc = fill_exchange_args(&P.x, world, rank, peers, max_rows, epoch, rows);
+    if (rc != HM_OK) return rc;
+    P.local = local_keys; P.local_groups = local_groups; P.out = out; P.rows = rows;
+    // the grid covers max_rows (not just rows) so that every rank runs the same CTAs and flags
+    hm_exchange_merge_kernel<<<(unsigned)exchange_blocks(max_rows), kExchangeRows, 0, stream>>>(P);
     HM_CUDA_CHECK(cudaGetLastError());
     return HM_OK;
 }

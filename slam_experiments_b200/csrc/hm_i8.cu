@@ -113,6 +113,7 @@ struct I8Params {
     unsigned long long* final_out;   // [batch][nq][2]: written by the last CTA of each query block when merging in-kernel
     unsigned* counters;              // [batch][qblocks] arrival counters (zeroed by the launcher), null = no in-kernel merge
     int splits;
+    ExchangeArgs xch;                // xch.world > 1: the last CTA also exchanges with the peer GPUs (sharded database)
     long long q_blocks_valid;        // 256-row blocks present in qprep (CTAs beyond it are cluster padding)
     long long* trace;                // development aid (HM_I8_TRACE): per-tile clock64 stamps of CTA 0, else null
 };
@@ -386,11 +387,12 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
         int* flag = reinterpret_cast<int*>(tmem_base_slot + 1);
         if (last_cta_arrives(&P.counters[(long long)b * gridDim.x + qb], (unsigned)P.splits, flag)) {
             const long long row = (long long)qb * kBlockM + threadIdx.x;
-            if (threadIdx.x < kBlockM && row < P.nq) {
-                unsigned long long k1 = kNoMatch, k2 = kNoMatch;
-                fold_partials(P.out, P.splits, P.out_split_stride, (long long)b * P.nq + row, k1, k2);
-                *reinterpret_cast<ulonglong2*>(P.final_out + ((long long)b * P.nq + row) * 2) = make_ulonglong2(k1, k2);
-            }
+            const bool has_row = threadIdx.x < kBlockM && row < P.nq;
+            ulonglong2 k = make_ulonglong2(kNoMatch, kNoMatch);
+            if (has_row) fold_partials(P.out, P.splits, P.out_split_stride, (long long)b * P.nq + row, k.x, k.y);
+            // sharded database: push to the peer GPUs, wait for theirs, merge -- still inside this launch
+            if (P.xch.world > 1) k = exchange_and_merge(P.xch, row, has_row, k, qb);
+            if (has_row) *reinterpret_cast<ulonglong2*>(P.final_out + ((long long)b * P.nq + row) * 2) = k;
         }
     }
 }
@@ -513,7 +515,7 @@ size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, b
 int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
                             unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
                             int sm_count, cudaStream_t stream, const unsigned long long** out_partials,
-                            int* out_groups)
+                            int* out_groups, const ExchangeArgs* exchange)
 {
     static bool attr_set = false;
     if (!attr_set) {
@@ -555,12 +557,23 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
     if (pl.splits > 1 || keep_partials) {
         P.out = partials;
         P.out_split_stride = rows * 2;
-        if (!keep_partials) {              // merge in-kernel: the last CTA per query block writes `out`
-            P.counters = counters;
-            P.final_out = out;
-            HM_CUDA_CHECK(cudaMemsetAsync(counters, 0, cbytes, stream));
+    }
+    const bool fused_exchange = exchange && exchange->world > 1;
+    if (fused_exchange) {
+        if (batch != 1 || keep_partials) {
+            set_error("fused exchange needs batch == 1 and an output buffer");
+            return HM_ERR_INVALID_ARGUMENT;
         }
-    } else {
+        static_assert(kBlockM == kExchangeRows, "flag granularity = query block");
+        P.xch = *exchange;
+        P.out = partials;                  // even with one split: the exchange runs in the last-CTA path
+        P.out_split_stride = rows * 2;
+    }
+    if ((pl.splits > 1 || fused_exchange) && !keep_partials) {   // merge in-kernel: last CTA per query block writes `out`
+        P.counters = counters;
+        P.final_out = out;
+        HM_CUDA_CHECK(cudaMemsetAsync(counters, 0, cbytes, stream));
+    } else if (!(pl.splits > 1 || keep_partials)) {
         P.out = out;
         P.out_split_stride = 0;
     }

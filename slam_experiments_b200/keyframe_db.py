@@ -13,6 +13,7 @@ rank for 2000 queries) over NCCL / NVLink, followed by ``hm_merge_top2``.  Unsig
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -51,6 +52,9 @@ class NativeOps:
     def __init__(self, device=None, variant: str = "auto"):
         self.device = nat.require_cuda(device)
         self.variant = variant
+        # "in_knn": exchange folded into the k-NN kernel's last-CTA merge (one launch);
+        # "separate": hm_exchange_merge as its own launch after the k-NN kernel
+        self.exchange_kernel = os.environ.get("HM_EXCHANGE_KERNEL", "in_knn")
         self._staging = _Staging()
         nat.lib()
 
@@ -112,15 +116,17 @@ class NativeOps:
             return "nccl"
 
     def local_knn2_exchange(self, query: torch.Tensor, shard, train_base: int, group) -> torch.Tensor:
-        """Local k-NN + exchange with the split merge folded into the exchange kernel (2 launches + the
-        query expansion per step instead of 4)."""
+        """Local k-NN + exchange + merge: one k-NN launch (plus the query expansion) per step."""
         x = getattr(self, "_xch", None)
         nq = query.shape[0]
         if x is None or shard["prepared"] is None or not (0 < nq <= x["max_rows"]):
             return self.gather_merge(self.local_knn2(query, shard, train_base), group)
         qprep = nat.prepare(query)
-        ptr, groups = nat.knn2_partials_prepared(qprep, nq, shard["prepared"], shard["nt"], train_base)
         x["epoch"] += 1
+        if self.exchange_kernel == "in_knn":
+            return nat.knn2_prepared_exchange(qprep, nq, shard["prepared"], shard["nt"], train_base, x["world"],
+                                              x["rank"], x["ptrs"], x["max_rows"], x["epoch"])
+        ptr, groups = nat.knn2_partials_prepared(qprep, nq, shard["prepared"], shard["nt"], train_base)
         return nat.exchange_merge(ptr, x["world"], x["rank"], x["ptrs"], x["max_rows"], x["epoch"], rows=nq,
                                   groups=groups, device=self.device)
 
