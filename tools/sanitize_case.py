@@ -1,0 +1,22 @@
+"""Small end-to-end case for compute-sanitizer (one tool per gpurun call, see B200_PROFILING.md)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from slam_experiments_b200 import _native as nat, synth
+from oracle import c_oracle
+
+ok = True
+for nq, nt in ((300, 700), (129, 1030), (513, 257)):
+    q, t = synth.uniform(nq, nq), synth.uniform(nt, nt + 1)
+    qd, td = torch.from_numpy(q).cuda(), torch.from_numpy(t).cuda()
+    exp = c_oracle.knn2_keys(q, t)
+    for v in ("popc", "i8"):
+        got = nat.knn2_keys(qd, td, variant=v).cpu().numpy().view(np.uint64)
+        ok &= bool(np.array_equal(got, exp))
+    oq, ot, od, cnt = nat.match_fused(qd[None], td[None], ratio=0.8, cross_check=True, variant="i8")
+    eq, et, ed = c_oracle.pipeline(q, t, 0.8, True)
+    n = int(cnt[0])
+    ok &= n == len(eq) and bool(np.array_equal(oq[0, :n].cpu().numpy(), eq))
+torch.cuda.synchronize()
+print("SANITIZE_CASE", "OK" if ok else "MISMATCH")
+sys.exit(0 if ok else 1)
