@@ -1,0 +1,151 @@
+"""Host-side mirror of the reference code either side of the matcher call (SURVEY.md 8a rows a5-a7,
+8f ranks 1-2): descriptor packing, the `_match_features` call site, and the consumers of
+``queryIdx`` / ``trainIdx``.
+
+The reference's own versions are Python loops over ``Feature`` objects:
+
+* ``Frame.get_descriptors`` (`/root/reference/primitives.py:200-205`) copies each feature's 32-byte
+  descriptor into a fresh ``(N, 32) uint8`` array on every call (0.7 ms at 2,000 features) and
+  returns ``np.array([])`` -- shape ``(0,)``, float64 -- for a frame without features;
+* ``Frontend._match_features`` (`/root/reference/frontend.py:181-187`) packs the last and the
+  current frame and calls ``matcher.match(desc_last, desc_cur)`` (train = last frame);
+* the consumers (`frontend.py:174-177,194,205-207`; `utils.py:13-19,41-47`) only index
+  ``last.features[m.trainIdx]`` and ``current.features[m.queryIdx]``.
+
+``get_descriptors`` / ``match_features`` / ``propagate_map_points`` reproduce those semantics
+exactly and work on the reference's own ``Frame`` / ``Feature`` objects (duck-typed: anything with
+``.features`` whose items have ``.descriptor``, ``.keypoint.pt`` / ``.position`` and ``.map_point``).
+``FrameDescriptorStore`` is the device-resident replacement for the per-call repacking: every
+frame's descriptors are uploaded once when the frame is created, so frame-to-frame tracking moves
+only the new frame (64 KB at 2,000 features) and the train side is already in HBM.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Any, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from .feature_matchers import BruteForceFeatureMatcher, MatcherError, _build_dmatches
+
+
+def get_descriptors(features: Sequence[Any]) -> np.ndarray:
+    """``Frame.get_descriptors`` (`primitives.py:200-205`): ``np.array([f.descriptor for f in features])``;
+    an empty feature list gives ``np.array([])`` exactly like the reference."""
+    return np.array([f.descriptor for f in features])
+
+
+def match_features(feature_matcher, last_frame, current_frame, dist_threshold: Optional[float] = None):
+    """``Frontend._match_features`` (`frontend.py:181-187`): train = last frame, query = current frame."""
+    desc_last = last_frame.get_descriptors() if hasattr(last_frame, "get_descriptors") else get_descriptors(last_frame.features)
+    desc_cur = current_frame.get_descriptors() if hasattr(current_frame, "get_descriptors") else get_descriptors(current_frame.features)
+    if dist_threshold is None:
+        return feature_matcher.match(desc_last, desc_cur)
+    return feature_matcher.match(desc_last, desc_cur, dist_threshold)
+
+
+def propagate_map_points(matches, last_features: Sequence[Any], current_features: Sequence[Any]) -> int:
+    """The consumer loop of `frontend.py:174-177`: copy ``map_point`` from the matched feature of the
+    last frame to the current frame's feature.  ``matches`` is a DMatch sequence or a
+    ``(queryIdx, trainIdx, ...)`` tuple of arrays.  Returns the number of propagated points."""
+    if isinstance(matches, tuple) and len(matches) >= 2 and isinstance(matches[0], np.ndarray):
+        pairs = zip(matches[0].tolist(), matches[1].tolist())
+    else:
+        pairs = ((m.queryIdx, m.trainIdx) for m in matches)
+    n = 0
+    for q, t in pairs:
+        map_point = last_features[t].map_point
+        if map_point:
+            current_features[q].map_point = map_point
+            n += 1
+    return n
+
+
+def keypoint_array(features: Sequence[Any]) -> np.ndarray:
+    """``(N, 2) int32`` pixel positions, as ``Feature.position`` (`primitives.py:108-110`) truncates them."""
+    if len(features) == 0:
+        return np.empty((0, 2), np.int32)
+    return np.array([f.keypoint.pt for f in features], dtype=np.float64).astype(np.int32)
+
+
+def matched_point_arrays(q_idx: np.ndarray, t_idx: np.ndarray, source_positions: np.ndarray,
+                         query_positions: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Packed ``(M, 2)`` arrays for ``cv2.findEssentialMat`` / ``triangulatePoints``: the two
+    list-building loops of `utils.py:13-19` and `:41-47` as two gathers (source = train frame)."""
+    return source_positions[np.asarray(t_idx)], query_positions[np.asarray(q_idx)]
+
+
+class FrameDescriptorStore:
+    """Device-resident descriptors of recent frames.
+
+    ``put(frame_id, descriptors)`` uploads a frame once (pinned staging, async copy); ``match(last_id,
+    current_id)`` runs the fused pipeline on the two resident arrays -- no host repacking, no H2D for
+    the train side.  Keeps at most ``capacity`` frames (oldest evicted), like the reference's 7 active
+    keyframes (`backend.py:11`).
+    """
+
+    def __init__(self, capacity: int = 8, *, ratio: Optional[float] = None, cross_check: bool = False,
+                 device=None, variant: str = "auto"):
+        self.device = nat.require_cuda(device)
+        self.capacity = int(capacity)
+        self.ratio, self.cross_check, self.variant = ratio, bool(cross_check), variant
+        self._frames: "OrderedDict[Any, torch.Tensor]" = OrderedDict()
+        self._pin: Optional[torch.Tensor] = None
+
+    def __contains__(self, frame_id) -> bool:
+        return frame_id in self._frames
+
+    def __len__(self) -> int:
+        return len(self._frames)
+
+    def put(self, frame_id, descriptors) -> torch.Tensor:
+        a = np.asarray(descriptors) if not isinstance(descriptors, torch.Tensor) else descriptors
+        if isinstance(a, np.ndarray):
+            if a.size == 0:
+                a = np.empty((0, nat.DESC_BYTES), np.uint8)       # a frame without features
+            if a.dtype != np.uint8 or a.ndim != 2 or a.shape[1] != nat.DESC_BYTES:
+                raise MatcherError(f"descriptors: expected uint8 [N, {nat.DESC_BYTES}], got {a.dtype} {a.shape}")
+            n = a.shape[0]
+            with torch.cuda.device(self.device):
+                if n == 0:
+                    t = torch.empty((0, nat.DESC_BYTES), dtype=torch.uint8, device=self.device)
+                else:
+                    nbytes = n * nat.DESC_BYTES
+                    if self._pin is None or self._pin.numel() < nbytes:
+                        self._pin = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
+                    host = self._pin[:nbytes].view(n, nat.DESC_BYTES)
+                    torch.cuda.current_stream(self.device).synchronize()   # the previous async copy has left the buffer
+                    host.numpy()[...] = a
+                    t = host.to(self.device, non_blocking=True)
+        else:
+            t = a.to(self.device).contiguous()
+        self._frames[frame_id] = t
+        self._frames.move_to_end(frame_id)
+        while len(self._frames) > self.capacity:
+            self._frames.popitem(last=False)
+        return t
+
+    def get(self, frame_id) -> torch.Tensor:
+        return self._frames[frame_id]
+
+    def match_tensors(self, last_id, current_id, dist_threshold: Optional[float] = None):
+        """``(queryIdx, trainIdx, distance)`` int32 arrays; query = current frame, train = last frame."""
+        t, q = self._frames[last_id], self._frames[current_id]
+        if q.shape[0] == 0 or t.shape[0] == 0:
+            e = np.empty(0, np.int32)
+            return e, e.copy(), e.copy()
+        oq, ot, od, cnt = nat.match_fused(q.unsqueeze(0), t.unsqueeze(0), ratio=self.ratio, cross_check=self.cross_check,
+                                          dist_threshold=dist_threshold if dist_threshold else None, variant=self.variant)
+        packed = torch.cat([cnt.view(1), oq.view(-1), ot.view(-1), od.view(-1)]).cpu().numpy()
+        n, nq = int(packed[0]), q.shape[0]
+        return packed[1:1 + n].copy(), packed[1 + nq:1 + nq + n].copy(), packed[1 + 2 * nq:1 + 2 * nq + n].copy()
+
+    def match(self, last_id, current_id, dist_threshold: Optional[float] = None):
+        """DMatch sequence with the reference's return convention (tuple, or list when filtered)."""
+        q, t, d = self.match_tensors(last_id, current_id, dist_threshold)
+        matches = _build_dmatches(q, t, d, 0)
+        if dist_threshold and len(matches) != 0:
+            return matches
+        return tuple(matches)

@@ -71,7 +71,41 @@ class NativeOps:
         nt = train.shape[0]
         use_i8 = self.variant == "i8" or (self.variant == "auto" and nt >= 65536)
         prepared = nat.prepare(train) if (use_i8 and nt > 0) else None
-        return {"bits": train, "prepared": prepared, "nt": nt}
+        return {"bits": train, "prepared": prepared, "nt": nt, "buf": None, "pbuf": None}
+
+    def append_rows(self, shard, rows: np.ndarray):
+        """Grow the resident shard by ``rows`` (a new keyframe): amortised-doubling device buffers, one
+        H2D of the new rows, and re-expansion of the touched 128-row blocks only."""
+        n = rows.shape[0]
+        if n == 0:
+            return shard
+        nt, new_nt = shard["nt"], shard["nt"] + n
+        with torch.cuda.device(self.device):
+            buf = shard.get("buf")
+            if buf is None or buf.shape[0] < new_nt:
+                cap = max(2 * new_nt, 4096)
+                nbuf = torch.empty((cap, nat.DESC_BYTES), dtype=torch.uint8, device=self.device)
+                if nt:
+                    nbuf[:nt].copy_(shard["bits"])
+                shard["buf"] = buf = nbuf
+                shard["pbuf"] = None
+            buf[nt:new_nt].copy_(torch.from_numpy(np.ascontiguousarray(rows, dtype=np.uint8)), non_blocking=False)
+            shard["bits"] = buf[:new_nt]
+            use_i8 = shard["prepared"] is not None or self.variant == "i8" or (self.variant == "auto" and new_nt >= 65536)
+            if use_i8:
+                need = nat.prepared_bytes(new_nt) + 512 * nat.PREPARED_ROW_BYTES
+                pbuf = shard.get("pbuf")
+                first = 0                                     # first row whose prepared image must be (re)written
+                if pbuf is None or pbuf.numel() < need:
+                    pbuf = torch.empty(max(need, nat.prepared_bytes(buf.shape[0]) + 512 * nat.PREPARED_ROW_BYTES),
+                                       dtype=torch.uint8, device=self.device)
+                    shard["pbuf"] = pbuf
+                elif shard["prepared"] is not None:
+                    first = (nt // 128) * 128                 # the partially filled block and everything after it
+                nat.prepare(buf[first:new_nt], out=pbuf[first * nat.PREPARED_ROW_BYTES:])
+                shard["prepared"] = pbuf
+            shard["nt"] = new_nt
+        return shard
 
     def local_knn2(self, query: torch.Tensor, shard, train_base: int) -> torch.Tensor:
         if shard["prepared"] is not None and query.shape[0] > 0:
@@ -177,6 +211,31 @@ class ShardedKeyframeDatabase:
             self.exchange_mode = self.ops.setup_exchange(group, world_size, rank, max_query_rows)
             if exchange == "fused" and self.exchange_mode != "fused":
                 raise nat.NativeError(f"fused exchange unavailable: {getattr(self.ops, '_xch_error', '?')}")
+
+    # ---- incremental growth (Map.insert_keyframe, `/root/reference/backend.py:31-37`) -----------------
+    def append_keyframe(self, descriptors: np.ndarray) -> int:
+        """Add one keyframe to the resident database; returns its ``imgIdx``.
+
+        Every rank calls this with the same array.  The keyframe joins the LAST rank's shard so that
+        shards stay contiguous keyframe ranges and a lower global row stays a lower
+        ``(imgIdx, trainIdx)`` -- the property the u64-min merge relies on."""
+        a = np.asarray(descriptors)
+        if a.size == 0:
+            a = np.empty((0, nat.DESC_BYTES), np.uint8)
+        if a.dtype != np.uint8 or a.ndim != 2 or a.shape[1] != nat.DESC_BYTES:
+            raise MatcherError("keyframe: expected uint8 [N, 32] descriptors")
+        if a.shape[0] >= (1 << 18):
+            raise MatcherError("too many rows in one train image (cv2: matchers.cpp:860)")
+        img = len(self.sizes)
+        if img + 1 >= 8192:
+            raise MatcherError("too many train images (cv2: matchers.cpp:856)")
+        self.sizes = np.append(self.sizes, a.shape[0])
+        self.starts = np.concatenate([[0], np.cumsum(self.sizes)])
+        if self.rank == self.world_size - 1:
+            self.shard = self.ops.append_rows(self.shard, a)
+            self.kf_hi += 1
+            self.row_hi += a.shape[0]
+        return img
 
     # ---- device-level API ---------------------------------------------------------------------
     def knn2_keys_device(self, query_dev: torch.Tensor) -> torch.Tensor:

@@ -1,0 +1,115 @@
+"""The callers either side of the matcher: descriptor packing, the
+`_match_features` call site and the `queryIdx`/`trainIdx` consumers, on reference-shaped objects."""
+import numpy as np
+import pytest
+import torch
+
+import slam_experiments_b200 as sx
+from conftest import load_golden, golden_files
+from oracle import hamming_oracle as ho
+
+cv2 = pytest.importorskip("cv2")
+
+
+class Feature:                      # /root/reference/primitives.py:92-112, the fields the path touches
+    def __init__(self, kp, descriptor):
+        self.keypoint, self.descriptor, self.map_point, self.is_outlier = kp, descriptor, None, False
+
+    @property
+    def position(self):
+        return np.array(self.keypoint.pt, dtype=np.int32)
+
+
+class Frame:                        # /root/reference/primitives.py:160-211
+    def __init__(self, descriptors, seed=0):
+        rng = np.random.default_rng(seed)
+        self.features = [Feature(cv2.KeyPoint(float(x), float(y), 31.0), d)
+                         for d, (x, y) in zip(descriptors, rng.uniform(0, 600, (len(descriptors), 2)))]
+
+    def get_descriptors(self):      # primitives.py:200-205
+        return np.array([f.descriptor for f in self.features])
+
+
+class RecordingMatcher(sx.FeatureMatcher):
+    def __init__(self):
+        self.calls = []
+
+    def match(self, source_descriptors, query_descriptors, dist_threshold=None):
+        self.calls.append((source_descriptors, query_descriptors, dist_threshold))
+        q, t, d = ho.reference_match(source_descriptors, query_descriptors, dist_threshold)
+        return tuple(cv2.DMatch(int(a), int(b), 0, float(c)) for a, b, c in zip(q, t, d))
+
+
+def test_get_descriptors_matches_reference_semantics():
+    g = load_golden(golden_files("c1_orb200.npz")[0])
+    f = Frame(g["train"])
+    d = sx.get_descriptors(f.features)
+    assert d.dtype == np.uint8 and d.shape == (200, 32) and np.array_equal(d, g["train"])
+    e = sx.get_descriptors([])
+    assert e.shape == (0,) and e.dtype == np.float64          # the reference's empty-frame quirk
+
+
+def test_match_features_argument_order_and_consumers():
+    g = load_golden(golden_files("c1_orb200.npz")[0])
+    last, cur = Frame(g["train"], 1), Frame(g["query"], 2)
+    m = RecordingMatcher()
+    matches = sx.match_features(m, last, cur)                 # frontend.py:185-187
+    src, qry, thr = m.calls[0]
+    assert np.array_equal(src, g["train"]) and np.array_equal(qry, g["query"]) and thr is None
+    assert [(x.queryIdx, x.trainIdx, int(x.distance)) for x in matches] == [tuple(r) for r in g["ref_match"][:, [0, 1, 3]].tolist()]
+    # consumers: frontend.py:174-177
+    for i, f in enumerate(last.features):
+        f.map_point = ("mp", i) if i % 3 == 0 else None
+    n = sx.propagate_map_points(matches, last.features, cur.features)
+    exp = 0
+    for x in matches:
+        if x.trainIdx % 3 == 0:
+            assert cur.features[x.queryIdx].map_point is not None
+            exp += 1
+    assert n == exp
+    q, t = g["ref_match"][:, 0], g["ref_match"][:, 1]
+    for f in cur.features:
+        f.map_point = None
+    assert sx.propagate_map_points((q, t), last.features, cur.features) == exp
+    # utils.py:13-19: packed point arrays == the reference's list-building loops
+    sp, qp = sx.matched_point_arrays(q, t, sx.keypoint_array(last.features), sx.keypoint_array(cur.features))
+    ref_s = np.array([last.features[x.trainIdx].position for x in matches])
+    ref_q = np.array([cur.features[x.queryIdx].position for x in matches])
+    assert np.array_equal(sp, ref_s) and np.array_equal(qp, ref_q)
+    assert sx.keypoint_array([]).shape == (0, 2)
+
+
+@pytest.mark.gpu
+def test_dropin_through_the_call_site_and_resident_store():
+    """a5 on the GPU: `_match_features` with the B200 matcher injected == the reference's own output,
+    and the device-resident store gives the same matches without re-uploading the train frame."""
+    for name in ("c1_orb200.npz", "c1_orb2000.npz"):
+        g = load_golden(golden_files(name)[0])
+        last, cur = Frame(g["train"], 1), Frame(g["query"], 2)
+        matcher = sx.BruteForceFeatureMatcher(norm_type=cv2.NORM_HAMMING)
+        out = sx.match_features(matcher, last, cur)
+        rows = [(m.queryIdx, m.trainIdx, m.imgIdx, int(m.distance)) for m in out]
+        assert isinstance(out, tuple) and rows == [tuple(r) for r in g["ref_match"].tolist()]
+        out = sx.match_features(matcher, last, cur, 30.0)
+        assert isinstance(out, list) and len(out) == len(g["ref_match_thr30"])
+        empty = Frame([])
+        assert sx.match_features(matcher, last, empty) == ()          # current frame lost all features
+        with pytest.raises(cv2.error):
+            sx.match_features(matcher, empty, cur)                    # cv2 raises for an np.array([]) train set
+
+        store = sx.FrameDescriptorStore(capacity=3)
+        store.put("last", last.get_descriptors())
+        store.put("cur", cur.get_descriptors())
+        rows = [(m.queryIdx, m.trainIdx, m.imgIdx, int(m.distance)) for m in store.match("last", "cur")]
+        assert rows == [tuple(r) for r in g["ref_match"].tolist()]
+        thr = store.match("last", "cur", 30.0)
+        assert isinstance(thr, list) and [(m.queryIdx, m.trainIdx) for m in thr] == [tuple(r) for r in g["ref_match_thr30"][:, :2].tolist()]
+        store.put("none", np.array([]))
+        assert store.match("last", "none") == () and store.match("none", "cur") == ()
+        for i in range(4):
+            store.put(i, g["query"])
+        assert len(store) == 3 and "last" not in store
+        pipe = sx.FrameDescriptorStore(ratio=0.75, cross_check=True)
+        pipe.put(0, g["train"]); pipe.put(1, g["query"])
+        q, t, d = pipe.match_tensors(0, 1)
+        assert np.array_equal(np.stack([q, t, d], 1), g["pipe75"][:, [0, 1, 3]])

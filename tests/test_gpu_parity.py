@@ -188,6 +188,21 @@ def test_prepared_operands_resident_database():
     assert set(np.unique(img[: 128 * 256]).tolist()) <= {-1, 1}
 
 
+@pytest.mark.parametrize("variant", VARIANTS)
+def test_incremental_keyframe_database(variant):
+    """Resident database grown keyframe by keyframe (backend.py:31-37) == cv2 collection over all of them."""
+    rng = np.random.default_rng(8)
+    sizes = [300, 90, 1, 515, 0, 128, 127, 700]
+    kfs = [rng.integers(0, 3, (s, 32), dtype=np.uint8) for s in sizes]
+    q = rng.integers(0, 3, (150, 32), dtype=np.uint8)
+    db = sx.ShardedKeyframeDatabase(sizes[:1], kfs[:1], variant=variant)
+    for i in range(1, len(sizes)):
+        assert db.append_keyframe(kfs[i]) == i
+        img, loc, d = db.knn_tensors(q, 2)
+        eimg, eloc, ed = ho.collection_knn(q, kfs[:i + 1], 2)
+        assert np.array_equal(img, eimg) and np.array_equal(loc, eloc) and np.array_equal(d, ed), i
+
+
 def test_host_context_c_abi_only():
     ctx = nat.HostContext()
     rng = np.random.default_rng(2)

@@ -27,6 +27,10 @@ class OracleOps:
     def make_shard(self, train):
         return {"bits": train, "prepared": None, "nt": train.shape[0]}
 
+    def append_rows(self, shard, rows):
+        cat = np.concatenate([shard["bits"].numpy(), rows]) if shard["nt"] else rows
+        return self.make_shard(torch.from_numpy(np.ascontiguousarray(cat)))
+
     def local_knn2(self, query, shard, train_base):
         keys = ho.knn2_keys(query.numpy(), shard["bits"].numpy(), train_base=train_base)
         return torch.from_numpy(keys.view(np.int64))
@@ -92,6 +96,21 @@ def test_sharded_matches_whole_database(world):
     rows = bf.knnMatch(q, k=2)
     exp = np.array([[(m.imgIdx, m.trainIdx, int(m.distance)) for m in r] for r in rows])
     assert np.array_equal(exp[:, :, 0], img) and np.array_equal(exp[:, :, 1], loc) and np.array_equal(exp[:, :, 2], d)
+
+
+def test_append_keyframes_incrementally():
+    """Map.insert_keyframe-style growth: the database after N appends == the database built at once."""
+    sizes, kfs, q = make_db(seed=3, nkf=6)
+    db = ShardedKeyframeDatabase(sizes[:2], kfs[:2], ops=OracleOps())
+    for i in range(2, 6):
+        assert db.append_keyframe(kfs[i]) == i
+    assert db.append_keyframe(np.array([])) == 6                   # a keyframe without features
+    img, loc, d = db.knn_tensors(q, 2)
+    eimg, eloc, ed = ho.collection_knn(q, kfs + [np.empty((0, 32), np.uint8)], 2)
+    assert np.array_equal(img, eimg) and np.array_equal(loc, eloc) and np.array_equal(d, ed)
+    cv2 = pytest.importorskip("cv2")
+    with pytest.raises(cv2.error):
+        db.append_keyframe(np.zeros((3, 16), np.uint8))
 
 
 def test_single_rank_database_equals_collection_oracle():
