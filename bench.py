@@ -266,7 +266,7 @@ def run_b200(args):
     del local_kfs
     q_dev = torch.from_numpy(query).to(dev)
     nt_local = row_hi - row_lo
-    variant_used = "i8" if db.shard["prepared"] is not None else args.variant
+    variant_used = nat.VARIANT_NAMES[db.shard["tc"]] if db.shard["prepared"] is not None else args.variant
 
     # ---- correctness of what is timed (outside the timed region): sample of rows vs the oracle ----
     verified = None
@@ -331,18 +331,23 @@ def run_b200(args):
 
     # ---- roofline of the dominant kernel (this rank's shard), from the live CUDA-event timing -----------
     local_pairs = float(NQ) * nt_local
-    if variant_used == "i8":
+    if variant_used in ("i8", "f4"):
+        # 256 MAC = 512 ops per pair for both cores; kind::mxf4 issues them at twice the kind::i8 rate
         achieved = local_pairs * I8_OPS_PER_PAIR / (kern_ms_max * 1e-3) / 1e12
-        peak = 2.0 * peaks["bf16_tflops_sustained"]
-        roofline = {"bound": "tensor", "kernel": "hm_i8_knn2_kernel", "achieved": achieved, "peak": peak,
+        mult = 2.0 if variant_used == "i8" else 4.0
+        issue_peak = 4569.0 if variant_used == "i8" else 8838.0
+        row_bytes = 256 if variant_used == "i8" else 128
+        kind = "kind::i8" if variant_used == "i8" else "kind::mxf4"
+        peak = mult * peaks["bf16_tflops_sustained"]
+        roofline = {"bound": "tensor", "kernel": f"hm_{variant_used}_knn2_kernel", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                    "note": f"int8 ops (512/pair); peak = 2 x bf16_tflops_sustained of {peak_src} "
-                            "(kind::i8 issues at twice the bf16 rate)",
+                    "note": f"+/-1 multiply-add ops (512/pair); peak = {mult:g} x bf16_tflops_sustained of {peak_src} "
+                            f"({kind} issues at {mult:g}x the bf16 rate)",
                     "kernel_ms": kern_ms_max, "pairs_per_launch": local_pairs,
-                    "frac_of_mma_issue_peak": achieved / 4569.0,
-                    "mma_issue_peak_note": "4569 int8 TOP/s = tcgen05.mma kind::i8 issue loop at 1965 MHz "
-                                           "(tools/microbench.cu, profiles/r01_microbench_b200.json)",
-                    "hbm_gbs": (nt_local * 256 + NQ * 256) / (kern_ms_max * 1e-3) / 1e9}
+                    "frac_of_mma_issue_peak": achieved / issue_peak,
+                    "mma_issue_peak_note": f"{issue_peak:g} TOP/s = tcgen05.mma {kind} issue loop at 1965 MHz "
+                                           "(tools/microbench.cu, tools/microbench_fp4.cu, profiles/r01*_microbench*.json)",
+                    "hbm_gbs": (nt_local * row_bytes + NQ * row_bytes) / (kern_ms_max * 1e-3) / 1e9}
     else:
         sm = nat.sm_count()
         achieved = local_pairs * POPC_PER_PAIR / (kern_ms_max * 1e-3) / 1e12
@@ -363,7 +368,8 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": dict(c4_config(world), variant=variant_used, exchange=db.exchange_mode,
-                                                         db_format="train shard resident as +/-1 int8 (expanded once at add())"),
+                                                         db_format={"i8": "train shard resident as +/-1 int8 (expanded once at add())",
+                                                                    "f4": "train shard resident as +/-1 e2m1 (expanded once at add())"}.get(variant_used, "packed bits")),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * 32, "d2h_bytes_per_step": NQ * 16,
                 "ms_per_step": e2e_s * 1e3, "api": "ShardedKeyframeDatabase.knnMatch(query_numpy, 2) -> DMatch tuples",
@@ -401,7 +407,7 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--variant", default="auto", choices=["auto", "popc", "i8"])
+    ap.add_argument("--variant", default="auto", choices=["auto", "popc", "i8", "f4"])
     ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
     ap.add_argument("--n", type=int, default=65536, help="c3: N x N")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"])

@@ -45,12 +45,15 @@ extern "C" {
 #define HM_API __attribute__((visibility("default")))
 #endif
 
-#define HM_ABI_VERSION 1
+#define HM_ABI_VERSION 2
 #define HM_DESC_BYTES 32
 #define HM_DESC_BITS 256
 #define HM_NO_MATCH 0xFFFFFFFFFFFFFFFFull
-/* one descriptor expanded to +/-1 int8 for the tensor-core variant */
+/* one descriptor expanded to +/-1 int8 (HM_VARIANT_I8) / +/-1 e2m1 4-bit floats (HM_VARIANT_F4) */
 #define HM_PREPARED_ROW_BYTES 256
+#define HM_PREPARED_F4_ROW_BYTES 128
+/* the tensor-core core HM_VARIANT_AUTO resolves to (ncu evidence in DESIGN.md) */
+#define HM_DEFAULT_TENSOR_VARIANT 2
 /* prepared images are padded to whole tiles of this many rows */
 #define HM_PREPARED_TILE_ROWS 256
 
@@ -66,7 +69,9 @@ typedef enum hm_status {
 typedef enum hm_variant {
     HM_VARIANT_AUTO = 0, /* static per-shape table baked from ncu evidence */
     HM_VARIANT_POPC = 1, /* (a) LOP3 XOR + POPC on 32-bit words */
-    HM_VARIANT_I8 = 2    /* (b) tcgen05 kind::i8 GEMM on +/-1 expansion, H = (256 - dot) / 2 */
+    HM_VARIANT_I8 = 2,   /* (b) tcgen05 kind::i8 GEMM on +/-1 expansion, H = (256 - dot) / 2 */
+    HM_VARIANT_F4 = 3    /* (b') same GEMM through tcgen05 kind::mxf4: +/-1 as e2m1, unit block scales, exact
+                            fp32 dot products, twice the kind::i8 issue rate and half the operand bytes */
 } hm_variant;
 
 /* flags of hm_filter_matches / hm_match_fused */
@@ -87,7 +92,7 @@ HM_API size_t hm_workspace_bytes(int64_t nq, int64_t nt, int batch, int variant)
 /* ---- measurement hook ---------------------------------------------------------------- */
 /* When both are non-NULL (cudaEvent_t as void*), every later k-NN call of this thread records
  * `start` immediately before and `stop` immediately after the launch of its dominant kernel
- * (hm_popc_knn2_kernel or hm_i8_knn2_kernel) on the call's stream, so bench.py can time that
+ * (hm_popc_knn2_kernel, hm_i8_knn2_kernel or hm_f4_knn2_kernel) on the call's stream, so bench.py can time that
  * kernel alone with CUDA events.  Pass NULLs to switch it off.  Not part of the data path. */
 HM_API void hm_profile_events(void* start_event, void* stop_event);
 
@@ -108,24 +113,28 @@ HM_API int hm_knn2_batched(const uint8_t* query, int64_t nq, int64_t q_stride, i
                            int batch, uint64_t* out_keys,
                            int variant, void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- tensor-core operand preparation (resident keyframe database) --------------------- */
-/* bytes of the prepared (+/-1 int8, tiled, 128B-swizzled) image of n descriptors */
-HM_API size_t hm_prepared_bytes(int64_t n);
-/* expand n packed descriptors into `prepared` (hm_prepared_bytes(n) bytes) */
-HM_API int hm_prepare(const uint8_t* bits, int64_t n, int64_t stride, void* prepared, void* stream);
+/* ---- tensor-core operand preparation (resident keyframe database) ---------------------
+ * `variant` selects the operand format: HM_VARIANT_I8, HM_VARIANT_F4, or HM_VARIANT_AUTO = the
+ * default tensor-core core (hm_default_tensor_variant()).  A prepared image must be consumed with the
+ * variant it was prepared for. */
+HM_API int hm_default_tensor_variant(void);
+/* bytes of the prepared (+/-1, tiled, 128B-swizzled) image of n descriptors */
+HM_API size_t hm_prepared_bytes(int64_t n, int variant);
+/* expand n packed descriptors into `prepared` (hm_prepared_bytes(n, variant) bytes) */
+HM_API int hm_prepare(const uint8_t* bits, int64_t n, int64_t stride, void* prepared, int variant, void* stream);
 /* scratch bytes hm_knn2_prepared / hm_knn2_prepared_partials need (no operand expansion inside) */
-HM_API size_t hm_prepared_workspace_bytes(int64_t nq, int64_t nt);
+HM_API size_t hm_prepared_workspace_bytes(int64_t nq, int64_t nt, int variant);
 /* k-NN over operands prepared once (train side of a keyframe database stays resident) */
 HM_API int hm_knn2_prepared(const void* query_prepared, int64_t nq,
                             const void* train_prepared, int64_t nt,
-                            uint64_t train_base, uint64_t* out_keys,
+                            uint64_t train_base, uint64_t* out_keys, int variant,
                             void* workspace, size_t workspace_bytes, void* stream);
 
 /* Same k-NN, but the per-train-split partial keys are left unmerged in the workspace:
  * *out_partials -> [*out_groups][nq][2] (valid until the workspace is reused on the stream).
  * Feed them to hm_exchange_merge (or hm_merge_top2) to save one launch on the sharded path. */
 HM_API int hm_knn2_prepared_partials(const void* query_prepared, int64_t nq,
-                                     const void* train_prepared, int64_t nt, uint64_t train_base,
+                                     const void* train_prepared, int64_t nt, uint64_t train_base, int variant,
                                      void* workspace, size_t workspace_bytes, void* stream,
                                      const uint64_t** out_partials, int* out_groups);
 
@@ -158,7 +167,7 @@ HM_API int hm_exchange_merge(const uint64_t* local_keys, int local_groups, int64
 HM_API int hm_knn2_prepared_exchange(const void* query_prepared, int64_t nq,
                                      const void* train_prepared, int64_t nt, uint64_t train_base,
                                      int world, int rank, void* const* peer_buffers_host, int64_t max_rows,
-                                     uint32_t epoch, uint64_t* out_keys,
+                                     uint32_t epoch, uint64_t* out_keys, int variant,
                                      void* workspace, size_t workspace_bytes, void* stream);
 
 /* Ratio test / mutual check / reference distance filter + ordered compaction, per problem.

@@ -19,18 +19,19 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO_PATH = os.path.join(HERE, "libhm_matcher.so")
 
 HM_OK = 0
-VARIANT_AUTO, VARIANT_POPC, VARIANT_I8 = 0, 1, 2
-VARIANTS = {"auto": VARIANT_AUTO, "popc": VARIANT_POPC, "i8": VARIANT_I8,
-            None: VARIANT_AUTO, 0: 0, 1: 1, 2: 2}
+VARIANT_AUTO, VARIANT_POPC, VARIANT_I8, VARIANT_F4 = 0, 1, 2, 3
+VARIANTS = {"auto": VARIANT_AUTO, "popc": VARIANT_POPC, "i8": VARIANT_I8, "f4": VARIANT_F4,
+            None: VARIANT_AUTO, 0: 0, 1: 1, 2: 2, 3: 3}
+VARIANT_NAMES = {VARIANT_POPC: "popc", VARIANT_I8: "i8", VARIANT_F4: "f4"}
 FLAG_RATIO, FLAG_MUTUAL, FLAG_DIST_THRESHOLD = 1, 2, 4
 NO_MATCH = 0xFFFFFFFFFFFFFFFF
 DESC_BYTES = 32
-PREPARED_ROW_BYTES = 256
+PREPARED_ROW_BYTES = {VARIANT_I8: 256, VARIANT_F4: 128}
 
 # every symbol include/hm_matcher.h declares (tests check the library exports all of them)
 EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
-    "hm_knn2", "hm_knn2_batched", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials", "hm_knn2_prepared_exchange",
+    "hm_knn2", "hm_knn2_batched", "hm_default_tensor_variant", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials", "hm_knn2_prepared_exchange",
     "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host",
 )
@@ -60,14 +61,15 @@ def _declare(L):
     L.hm_knn2.argtypes = [vp, i64, i64, vp, i64, i64, u64, vp, ci, vp, sz, vp]
     L.hm_knn2_batched.restype = ci
     L.hm_knn2_batched.argtypes = [vp, i64, i64, i64, vp, i64, i64, i64, ci, vp, ci, vp, sz, vp]
+    L.hm_default_tensor_variant.restype = ci
     L.hm_prepared_bytes.restype = sz
-    L.hm_prepared_bytes.argtypes = [i64]
+    L.hm_prepared_bytes.argtypes = [i64, ci]
     L.hm_prepared_workspace_bytes.restype = sz
-    L.hm_prepared_workspace_bytes.argtypes = [i64, i64]
+    L.hm_prepared_workspace_bytes.argtypes = [i64, i64, ci]
     L.hm_prepare.restype = ci
-    L.hm_prepare.argtypes = [vp, i64, i64, vp, vp]
+    L.hm_prepare.argtypes = [vp, i64, i64, vp, ci, vp]
     L.hm_knn2_prepared.restype = ci
-    L.hm_knn2_prepared.argtypes = [vp, i64, vp, i64, u64, vp, vp, sz, vp]
+    L.hm_knn2_prepared.argtypes = [vp, i64, vp, i64, u64, vp, ci, vp, sz, vp]
     L.hm_merge_top2.restype = ci
     L.hm_merge_top2.argtypes = [vp, ci, i64, vp, vp]
     L.hm_exchange_bytes.restype = sz
@@ -75,9 +77,9 @@ def _declare(L):
     L.hm_exchange_merge.restype = ci
     L.hm_exchange_merge.argtypes = [vp, ci, i64, ci, ci, vp, i64, c.c_uint32, vp, vp]
     L.hm_knn2_prepared_exchange.restype = ci
-    L.hm_knn2_prepared_exchange.argtypes = [vp, i64, vp, i64, u64, ci, ci, vp, i64, c.c_uint32, vp, vp, sz, vp]
+    L.hm_knn2_prepared_exchange.argtypes = [vp, i64, vp, i64, u64, ci, ci, vp, i64, c.c_uint32, vp, ci, vp, sz, vp]
     L.hm_knn2_prepared_partials.restype = ci
-    L.hm_knn2_prepared_partials.argtypes = [vp, i64, vp, i64, u64, vp, sz, vp, c.POINTER(vp), c.POINTER(ci)]
+    L.hm_knn2_prepared_partials.argtypes = [vp, i64, vp, i64, u64, ci, vp, sz, vp, c.POINTER(vp), c.POINTER(ci)]
     L.hm_filter_matches.restype = ci
     L.hm_filter_matches.argtypes = [vp, i64, vp, i64, ci, cu, vp, c.c_double, vp, vp, vp, vp, vp]
     L.hm_match_fused.restype = ci
@@ -133,7 +135,17 @@ def variant_id(variant) -> int:
     try:
         return VARIANTS[variant]
     except KeyError:
-        raise ValueError(f"unknown variant {variant!r}; expected 'auto', 'popc' or 'i8'") from None
+        raise ValueError(f"unknown variant {variant!r}; expected 'auto', 'popc', 'i8' or 'f4'") from None
+
+
+def tensor_variant(variant="auto") -> int:
+    """The tensor-core core (``VARIANT_I8`` / ``VARIANT_F4``) a prepared-operand call uses."""
+    v = variant_id(variant)
+    if v == VARIANT_AUTO:
+        v = lib().hm_default_tensor_variant()
+    if v not in (VARIANT_I8, VARIANT_F4):
+        raise ValueError(f"variant {variant!r} has no prepared operand format")
+    return v
 
 
 # ---- workspace cache: one growing uint8 tensor per (device, stream) ---------------------------
@@ -203,37 +215,40 @@ def knn2_keys_batched(query: torch.Tensor, train: torch.Tensor, variant="auto",
     return out
 
 
-def prepared_bytes(n: int) -> int:
-    return int(lib().hm_prepared_bytes(n))
+def prepared_bytes(n: int, variant="auto") -> int:
+    return int(lib().hm_prepared_bytes(n, tensor_variant(variant)))
 
 
-def prepare(bits: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """``hm_prepare``: expand packed descriptors to the +/-1 int8 tensor-core image."""
+def prepare(bits: torch.Tensor, out: Optional[torch.Tensor] = None, variant="auto") -> torch.Tensor:
+    """``hm_prepare``: expand packed descriptors to the +/-1 tensor-core image of ``variant``
+    (int8 for ``"i8"``, e2m1 for ``"f4"``)."""
     _check_desc(bits, "bits")
     dev = bits.device
     n = bits.shape[0]
-    nbytes = prepared_bytes(n)
+    v = tensor_variant(variant)
+    nbytes = prepared_bytes(n, v)
     if out is None:
         out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     elif out.numel() < nbytes:
         raise ValueError("prepared buffer too small")
     with torch.cuda.device(dev):
-        check(lib().hm_prepare(bits.data_ptr(), n, bits.stride(0) if n else DESC_BYTES, out.data_ptr(),
+        check(lib().hm_prepare(bits.data_ptr(), n, bits.stride(0) if n else DESC_BYTES, out.data_ptr(), v,
                                _stream_ptr(dev)), "hm_prepare")
     return out
 
 
 def knn2_keys_prepared(query_prepared: torch.Tensor, nq: int, train_prepared: torch.Tensor, nt: int,
-                       train_base: int = 0, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                       train_base: int = 0, out: Optional[torch.Tensor] = None, variant="auto") -> torch.Tensor:
     dev = query_prepared.device
     if out is None:
         out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
+    v = tensor_variant(variant)
     L = lib()
     with torch.cuda.device(dev):
-        wsb = L.hm_prepared_workspace_bytes(nq, nt)
+        wsb = L.hm_prepared_workspace_bytes(nq, nt, v)
         ws = workspace(wsb, dev)
         check(L.hm_knn2_prepared(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
-                                 out.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "hm_knn2_prepared")
+                                 out.data_ptr(), v, ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "hm_knn2_prepared")
     return out
 
 
@@ -276,34 +291,36 @@ def exchange_merge(local_keys, world: int, rank: int, peer_ptrs, max_rows: int, 
 
 def knn2_prepared_exchange(query_prepared: torch.Tensor, nq: int, train_prepared: torch.Tensor, nt: int,
                            train_base: int, world: int, rank: int, peer_ptrs, max_rows: int, epoch: int,
-                           out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                           out: Optional[torch.Tensor] = None, variant="auto") -> torch.Tensor:
     """``hm_knn2_prepared_exchange``: local k-NN + cross-GPU exchange + merge in one launch."""
     dev = query_prepared.device
     if out is None:
         out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
     arr = peer_ptrs if isinstance(peer_ptrs, ctypes.Array) else (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
+    v = tensor_variant(variant)
     L = lib()
     with torch.cuda.device(dev):
-        wsb = L.hm_prepared_workspace_bytes(nq, nt)
+        wsb = L.hm_prepared_workspace_bytes(nq, nt, v)
         ws = workspace(wsb, dev)
         check(L.hm_knn2_prepared_exchange(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
-                                          world, rank, arr, max_rows, epoch, out.data_ptr(), ws.data_ptr(), ws.numel(),
-                                          _stream_ptr(dev)), "hm_knn2_prepared_exchange")
+                                          world, rank, arr, max_rows, epoch, out.data_ptr(), v, ws.data_ptr(),
+                                          ws.numel(), _stream_ptr(dev)), "hm_knn2_prepared_exchange")
     return out
 
 
 def knn2_partials_prepared(query_prepared: torch.Tensor, nq: int, train_prepared: torch.Tensor, nt: int,
-                           train_base: int = 0):
+                           train_base: int = 0, variant="auto"):
     """``hm_knn2_prepared_partials``: returns ``(device_ptr, groups)`` of the unmerged per-split keys,
     valid until the cached workspace is reused on this stream."""
     dev = query_prepared.device
     L = lib()
     parts, groups = ctypes.c_void_p(), ctypes.c_int(0)
+    v = tensor_variant(variant)
     with torch.cuda.device(dev):
-        wsb = L.hm_prepared_workspace_bytes(nq, nt)
+        wsb = L.hm_prepared_workspace_bytes(nq, nt, v)
         ws = workspace(wsb, dev)
         check(L.hm_knn2_prepared_partials(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
-                                          ws.data_ptr(), ws.numel(), _stream_ptr(dev), ctypes.byref(parts),
+                                          v, ws.data_ptr(), ws.numel(), _stream_ptr(dev), ctypes.byref(parts),
                                           ctypes.byref(groups)), "hm_knn2_prepared_partials")
     return parts.value, groups.value
 
@@ -391,7 +408,7 @@ def sm_count() -> int:
 
 
 def select_variant(nq: int, nt: int, batch: int = 1) -> str:
-    return {VARIANT_POPC: "popc", VARIANT_I8: "i8"}[lib().hm_select_variant(nq, nt, batch)]
+    return VARIANT_NAMES[lib().hm_select_variant(nq, nt, batch)]
 
 
 def split_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:

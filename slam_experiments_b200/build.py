@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libhm_matcher.so")
-SOURCES = ["hm_api.cu", "hm_popc.cu", "hm_i8.cu", "hm_epilogue.cu"]
+SOURCES = ["hm_api.cu", "hm_popc.cu", "hm_tc.cu", "hm_epilogue.cu"]
 HEADERS = ["hm_common.cuh", "hm_tcgen05.cuh"]
 
 

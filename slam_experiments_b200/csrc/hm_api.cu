@@ -3,6 +3,7 @@
 // device every compute entry point fails with HM_ERR_NO_DEVICE.
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -75,10 +76,21 @@ inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 // Static per-shape table ("variant selection"): the tensor-core variant pays an
 // operand-expansion pre-pass and needs >= 128 query rows per CTA; below ~3e7 pairs the POPC
 // kernel (one launch, train split over the grid) is launch/latency-bound and wins.
+// The tensor-core core AUTO resolves to.  HM_TENSOR_CORE=i8|f4 overrides it for experiments.
+int default_tensor_variant()
+{
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("HM_TENSOR_CORE");
+        v = (e && !strcmp(e, "i8")) ? HM_VARIANT_I8 : (e && !strcmp(e, "f4")) ? HM_VARIANT_F4 : HM_DEFAULT_TENSOR_VARIANT;
+    }
+    return v;
+}
+
 int select_variant(long long nq, long long nt, int batch)
 {
     const double pairs = (double)nq * (double)nt * (double)batch;
-    if (nq >= 64 && nt >= 256 && pairs >= 3.0e7) return HM_VARIANT_I8;
+    if (nq >= 64 && nt >= 256 && pairs >= 3.0e7) return default_tensor_variant();
     return HM_VARIANT_POPC;
 }
 
@@ -86,6 +98,15 @@ int resolve_variant(int variant, long long nq, long long nt, int batch)
 {
     if (variant == HM_VARIANT_AUTO) return select_variant(nq, nt, batch);
     return variant;
+}
+
+// prepared-operand entry points: AUTO = the default tensor core; POPC has no prepared form
+int resolve_tensor_variant(int variant)
+{
+    if (variant == HM_VARIANT_AUTO) return default_tensor_variant();
+    if (variant == HM_VARIANT_I8 || variant == HM_VARIANT_F4) return variant;
+    set_error("variant %d has no prepared operand format (expected HM_VARIANT_I8, HM_VARIANT_F4 or AUTO)", variant);
+    return HM_ERR_INVALID_ARGUMENT;
 }
 
 int check_rows(const void* p, long long n, long long stride, const char* what)
@@ -112,7 +133,8 @@ size_t knn_workspace(long long nq, long long nt, int batch, int variant, int sm_
     if (nq <= 0 || nt <= 0 || batch <= 0) return 0;
     size_t a = 0, b = 0;
     if (variant == HM_VARIANT_AUTO || variant == HM_VARIANT_POPC) a = popc_workspace_bytes(nq, nt, batch, sm_count);
-    if (variant == HM_VARIANT_AUTO || variant == HM_VARIANT_I8) b = i8_workspace_bytes(nq, nt, batch, sm_count, true);
+    if (variant == HM_VARIANT_AUTO) variant = default_tensor_variant();
+    if (variant == HM_VARIANT_I8 || variant == HM_VARIANT_F4) b = tc_workspace_bytes(nq, nt, batch, sm_count, true, variant);
     return align_up(a > b ? a : b);
 }
 
@@ -151,7 +173,8 @@ int knn2_dispatch(const KnnProblem& p, unsigned long long* out, int variant, voi
     const int v = resolve_variant(variant, p.nq, p.nt, p.batch);
     switch (v) {
         case HM_VARIANT_POPC: return launch_popc_knn2(p, out, ws, ws_bytes, di.sm_count, stream);
-        case HM_VARIANT_I8: return launch_i8_knn2(p, out, ws, ws_bytes, di.sm_count, stream);
+        case HM_VARIANT_I8:
+        case HM_VARIANT_F4: return launch_tc_knn2(p, out, ws, ws_bytes, di.sm_count, v, stream);
         default: set_error("unknown variant %d", variant); return HM_ERR_INVALID_ARGUMENT;
     }
 }
@@ -219,37 +242,49 @@ HM_API int hm_knn2_batched(const uint8_t* query, int64_t nq, int64_t q_stride, i
                          static_cast<cudaStream_t>(stream));
 }
 
-HM_API size_t hm_prepared_workspace_bytes(int64_t nq, int64_t nt)
+HM_API int hm_default_tensor_variant(void) { return default_tensor_variant(); }
+
+HM_API size_t hm_prepared_workspace_bytes(int64_t nq, int64_t nt, int variant)
 {
     DeviceInfo di;
     int sm = 148;
     if (device_info(&di) == HM_OK) sm = di.sm_count;
+    const int v = resolve_tensor_variant(variant);
+    if (v < 0) return 0;
     if (nq <= 0 || nt <= 0) return 256;
-    return align_up(i8_workspace_bytes(nq, nt, 1, sm, false));
+    return align_up(tc_workspace_bytes(nq, nt, 1, sm, false, v));
 }
 
-HM_API size_t hm_prepared_bytes(int64_t n) { return n > 0 ? prepared_bytes(n) : 0; }
+HM_API size_t hm_prepared_bytes(int64_t n, int variant)
+{
+    const int v = resolve_tensor_variant(variant);
+    return (n > 0 && v > 0) ? prepared_bytes(n, v) : 0;
+}
 
-HM_API int hm_prepare(const uint8_t* bits, int64_t n, int64_t stride, void* prepared, void* stream)
+HM_API int hm_prepare(const uint8_t* bits, int64_t n, int64_t stride, void* prepared, int variant, void* stream)
 {
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc != HM_OK) return rc;
+    const int v = resolve_tensor_variant(variant);
+    if (v < 0) return v;
     if ((rc = check_rows(bits, n, stride, "bits")) != HM_OK) return rc;
     if (n > 0 && (!prepared || (reinterpret_cast<uintptr_t>(prepared) & 15))) {
         set_error("prepared buffer must be non-null and 16-byte aligned");
         return HM_ERR_INVALID_ARGUMENT;
     }
-    return launch_prepare(bits, n, stride, 0, 1, prepared, static_cast<cudaStream_t>(stream));
+    return launch_prepare(bits, n, stride, 0, 1, prepared, v, static_cast<cudaStream_t>(stream));
 }
 
 HM_API int hm_knn2_prepared(const void* query_prepared, int64_t nq, const void* train_prepared, int64_t nt,
-                            uint64_t train_base, uint64_t* out_keys, void* workspace, size_t workspace_bytes,
-                            void* stream)
+                            uint64_t train_base, uint64_t* out_keys, int variant, void* workspace,
+                            size_t workspace_bytes, void* stream)
 {
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc != HM_OK) return rc;
+    const int v = resolve_tensor_variant(variant);
+    if (v < 0) return v;
     if (nq < 0 || nt < 0) {
         set_error("negative row count");
         return HM_ERR_INVALID_ARGUMENT;
@@ -266,46 +301,50 @@ HM_API int hm_knn2_prepared(const void* query_prepared, int64_t nq, const void* 
         set_error("prepared operands must be non-null and 16-byte aligned");
         return HM_ERR_INVALID_ARGUMENT;
     }
-    return launch_i8_knn2_prepared(query_prepared, nq, train_prepared, nt, 1, train_base,
+    return launch_tc_knn2_prepared(query_prepared, nq, train_prepared, nt, 1, train_base,
                                    reinterpret_cast<unsigned long long*>(out_keys), workspace, workspace_bytes,
-                                   di.sm_count, st);
+                                   di.sm_count, v, st);
 }
 
 HM_API int hm_knn2_prepared_partials(const void* query_prepared, int64_t nq, const void* train_prepared, int64_t nt,
-                                     uint64_t train_base, void* workspace, size_t workspace_bytes, void* stream,
-                                     const uint64_t** out_partials, int* out_groups)
+                                     uint64_t train_base, int variant, void* workspace, size_t workspace_bytes,
+                                     void* stream, const uint64_t** out_partials, int* out_groups)
 {
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc != HM_OK) return rc;
+    const int v = resolve_tensor_variant(variant);
+    if (v < 0) return v;
     if (nq <= 0 || nt <= 0 || !out_partials || !out_groups || !query_prepared || !train_prepared) {
         set_error("hm_knn2_prepared_partials: bad arguments");
         return HM_ERR_INVALID_ARGUMENT;
     }
     const unsigned long long* parts = nullptr;
-    rc = launch_i8_knn2_prepared(query_prepared, nq, train_prepared, nt, 1, train_base, nullptr, workspace,
-                                 workspace_bytes, di.sm_count, static_cast<cudaStream_t>(stream), &parts, out_groups);
+    rc = launch_tc_knn2_prepared(query_prepared, nq, train_prepared, nt, 1, train_base, nullptr, workspace,
+                                 workspace_bytes, di.sm_count, v, static_cast<cudaStream_t>(stream), &parts, out_groups);
     *out_partials = reinterpret_cast<const uint64_t*>(parts);
     return rc;
 }
 
 HM_API int hm_knn2_prepared_exchange(const void* query_prepared, int64_t nq, const void* train_prepared, int64_t nt,
                                      uint64_t train_base, int world, int rank, void* const* peer_buffers_host,
-                                     int64_t max_rows, uint32_t epoch, uint64_t* out_keys, void* workspace,
+                                     int64_t max_rows, uint32_t epoch, uint64_t* out_keys, int variant, void* workspace,
                                      size_t workspace_bytes, void* stream)
 {
     DeviceInfo di;
     int rc = device_info(&di);
     if (rc != HM_OK) return rc;
+    const int v = resolve_tensor_variant(variant);
+    if (v < 0) return v;
     if (nq <= 0 || nt <= 0 || !out_keys || !query_prepared || !train_prepared) {
         set_error("hm_knn2_prepared_exchange: bad arguments");
         return HM_ERR_INVALID_ARGUMENT;
     }
     ExchangeArgs x;
     if ((rc = fill_exchange_args(&x, world, rank, peer_buffers_host, max_rows, epoch, nq)) != HM_OK) return rc;
-    return launch_i8_knn2_prepared(query_prepared, nq, train_prepared, nt, 1, train_base,
+    return launch_tc_knn2_prepared(query_prepared, nq, train_prepared, nt, 1, train_base,
                                    reinterpret_cast<unsigned long long*>(out_keys), workspace, workspace_bytes,
-                                   di.sm_count, static_cast<cudaStream_t>(stream), nullptr, nullptr, &x);
+                                   di.sm_count, v, static_cast<cudaStream_t>(stream), nullptr, nullptr, &x);
 }
 
 HM_API int hm_merge_top2(const uint64_t* keys, int groups, int64_t rows, uint64_t* out_keys, void* stream)

@@ -192,22 +192,22 @@ int launch_popc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, siz
                      int sm_count, cudaStream_t stream);
 size_t popc_workspace_bytes(long long nq, long long nt, int batch, int sm_count);
 
-// (b) tcgen05 kind::i8 variant.
-size_t prepared_bytes(long long n);
+// (b) tensor-core variants (hm_tc.cu); `variant` is HM_VARIANT_I8 or HM_VARIANT_F4.
+size_t prepared_bytes(long long n, int variant);
 int launch_prepare(const uint8_t* bits, long long n, long long stride, long long batch_stride, int batch,
-                   void* prepared, cudaStream_t stream);
+                   void* prepared, int variant, cudaStream_t stream);
 // out == nullptr: leave the per-split partials in the workspace and report them through
 // out_partials / out_groups instead of merging
-int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
+int launch_tc_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
                             unsigned long long train_base, unsigned long long* out, void* ws,
-                            size_t ws_bytes, int sm_count, cudaStream_t stream,
+                            size_t ws_bytes, int sm_count, int variant, cudaStream_t stream,
                             const unsigned long long** out_partials = nullptr, int* out_groups = nullptr,
                             const ExchangeArgs* exchange = nullptr);
 int fill_exchange_args(ExchangeArgs* x, int world, int rank, void* const* peers, long long max_rows, unsigned epoch,
                        long long rows);
-size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare);
-int launch_i8_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count,
-                   cudaStream_t stream);
+size_t tc_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare, int variant);
+int launch_tc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count,
+                   int variant, cudaStream_t stream);
 
 // epilogues
 int launch_merge_top2(const unsigned long long* keys, int groups, long long rows, unsigned long long* out,

@@ -1,32 +1,39 @@
-// Variant (b): tcgen05 kind::i8 GEMM on the +/-1 expansion of the descriptors.
+// Tensor-core variants: a tcgen05 GEMM on the +/-1 expansion of the descriptors.
 //
-// dot(a, b) over the +/-1 int8 images of two 256-bit descriptors is 256 - 2*H, so the
-// exact Hamming distance is H = (256 - dot) / 2 and "nearest" is "largest dot".
+// dot(a, b) over the +/-1 images of two 256-bit descriptors is 256 - 2*H, so the exact Hamming
+// distance is H = (256 - dot) / 2 and "nearest" is "largest dot".  Two cores share one kernel body:
 //
-// One CTA owns 256 query rows (two 128-row A blocks, resident in shared memory, 64 KB) and
-// streams 128-row train tiles (B operand, 32 KB each) through a 4-deep bulk-async-copy ring.
-// Per tile a single elected thread issues 2 x 8 tcgen05.mma (M=128, N=128, K=32 bytes) into one of
-// two TMEM accumulator buffers (2 query blocks x 128 columns each; 512 columns in total); eight
-// epilogue warps (one per 32 query rows) read the other buffer with tcgen05.ld (thread = query
-// row, registers = train columns) and keep the running top-2 in registers, so the distance
-// tile never leaves the SM.
+//   (b)  kind::i8    +/-1 as int8, 256 B per descriptor, K = 32 elements per MMA, s32 accumulators
+//                    (the variant the north star names);
+//   (b') kind::mxf4  +/-1 as e2m1 4-bit floats (+1.0 = 0x2, -1.0 = 0xA), 128 B per descriptor, K = 64
+//                    elements per MMA, every ue8m0 block scale = 1.0, fp32 accumulators.  The dot
+//                    products are small integers, exact in fp32, and the instruction issues at twice
+//                    the kind::i8 rate (tools/microbench_fp4.cu: 16381 vs 8191 MAC/clk/SM, one
+//                    128x128x256 tile bit-exact incl. dot = +/-256) with half the operand bytes.
 //
-// Why this shape (ncu, profiles/r01a_* and r01b_*): the +/-1 operands are 8x larger than the
-// packed bits, so with 128 query rows per CTA each 1024-cycle tile needs 64 KB of B -- 10 TB/s of
-// L2->SM traffic at speed, and two 64 KB stages cannot cover the ~2500-cycle load latency
-// (tensor pipe 58 % active, long-scoreboard stalls).  256 query rows per CTA halve the bytes per
-// MMA cycle (32 B/clk/SM) and leave room for four stages (128 KB in flight).  Optionally CTAs are
-// launched as thread-block clusters of 2 or 4 query blocks that share every train tile: each CTA
-// fetches 1/CS of the tile and multicasts it (cp.async.bulk ... .multicast::cluster), and a stage
-// is released by the multicast tcgen05.commit of all CS MMA issuers.
+// One CTA owns 256 query rows (two 128-row A blocks, resident in shared memory) and streams 128-row
+// train tiles (B operand) through a ring of bulk-async-copy stages.  Per (tile, query block) a single
+// elected thread issues the MMAs (M=128, N=128) into one of the 128-column TMEM accumulator units;
+// eight epilogue warps (one per 32 query rows) read finished units with tcgen05.ld (thread = query
+// row, registers = train columns) and keep the running top-2 in registers, so the distance tile never
+// leaves the SM.  kind::i8 uses four units (2 query blocks x 2 buffers = all 512 columns); kind::mxf4
+// rotates three units and keeps its scale factors in the last 128 columns.
+//
+// Why this shape (ncu, profiles/r01a_* .. r01g_*): the +/-1 operands are 8x (4x) larger than the
+// packed bits, so with 128 query rows per CTA each tile needs 64 B/clk/SM of L2->SM traffic and two
+// stages cannot cover the ~2500-cycle load latency.  256 query rows per CTA halve the bytes per MMA
+// cycle and leave room for 128 KB in flight.  CTAs are launched as thread-block clusters of 2 query
+// blocks that share every train tile: each CTA fetches 1/CS of the tile and multicasts it
+// (cp.async.bulk ... .multicast::cluster), and a stage is released by the multicast tcgen05.commit
+// of all CS MMA issuers.
 //
 // Replaces the same cv::batchDistance loop as hm_popc.cu
 // (/root/reference/feature_matchers.py:39 -> cv2.BFMatcher).
 //
-// Operands are "prepared" once by hm_prepare(): 256 bytes per descriptor, grouped in
-// blocks of 128 rows x 128 bytes (one K slab) laid out exactly as the UMMA K-major
-// SWIZZLE_128B shared-memory image; a 128-row block is [slab 0 | slab 1] = 32 contiguous KB, so
-// a train tile is ONE bulk copy (cp.async.bulk / UBLKCP) with no tensor map.
+// Operands are "prepared" once by hm_prepare(): rows grouped in blocks of 128, each block stored
+// exactly as the UMMA K-major SWIZZLE_128B shared-memory image (128-byte K slabs: two per row block
+// for int8, one for e2m1), so a train tile is ONE contiguous bulk copy with no tensor map.
+#include <math.h>
 #include <stdlib.h>
 
 #include "hm_common.cuh"
@@ -41,22 +48,58 @@ constexpr int kMBlocks = 2;                  // A blocks per CTA
 constexpr int kBlockM = kRowBlock * kMBlocks;   // 256 queries per CTA
 constexpr int kBlockN = kRowBlock;           // train rows per tile
 constexpr int kSlabBytes = kRowBlock * 128;  // 16 KB: 128 rows x 128 bytes of K
-constexpr int kRowBlockBytes = 2 * kSlabBytes;  // 32 KB: one prepared row block
 constexpr int kPadRows = HM_PREPARED_TILE_ROWS;
-constexpr int kStages = 4;
-constexpr int kABytes = kMBlocks * kRowBlockBytes;   // 64 KB
-constexpr int kBStageBytes = kRowBlockBytes;         // 32 KB
-constexpr int kTmemCols = 512;               // 2 buffers x 2 query blocks x 128 columns
+constexpr int kTmemCols = 512;
 constexpr int kEpilogueWarps = 4 * kMBlocks; // one per 32 query rows
 constexpr int kThreads = 32 * (2 + kEpilogueWarps);  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
-constexpr int kSmemBytes = 1024 + kABytes + kStages * kBStageBytes + 256;
 constexpr uint32_t kSpinLimit = 1u << 26;
 
 static_assert(kPadRows % kBlockN == 0 && kPadRows % kBlockM == 0, "prepared padding must cover whole tiles");
 
+// ---- the two cores ---------------------------------------------------------------------------
+struct CoreI8 {
+    using Acc = int;
+    static constexpr int kSlabs = 2;                         // 128-byte K slabs per row
+    static constexpr int kRowBytes = HM_PREPARED_ROW_BYTES;  // 256
+    static constexpr int kStages = 4;                        // 4 x 32 KB in flight
+    static constexpr int kUnits = 4;                         // accumulator units of 128 TMEM columns
+    static constexpr bool kScales = false;
+    static constexpr int kPrologueTiles = 4;                 // fixed per-CTA cost in tile times (split planning)
+    static __device__ __forceinline__ Acc lowest() { return INT_MIN; }
+    static __device__ __forceinline__ Acc from_bits(uint32_t x) { return (int)x; }
+    static __device__ __forceinline__ Acc max3(Acc a, Acc b, Acc c) { return __vimax3_s32(a, b, c); }
+    static __device__ __forceinline__ Acc max2(Acc a, Acc b) { return max(a, b); }
+    static __device__ __forceinline__ bool valid(Acc v) { return v != INT_MIN; }
+    static __device__ __forceinline__ unsigned distance(Acc v) { return (unsigned)((256 - v) >> 1); }
+};
+
+struct CoreF4 {
+    using Acc = float;
+    static constexpr int kSlabs = 1;
+    static constexpr int kRowBytes = HM_PREPARED_F4_ROW_BYTES;  // 128
+    static constexpr int kStages = 8;                        // 8 x 16 KB in flight (a tile lasts half as long)
+    static constexpr int kUnits = 3;                         // columns [0, 384); scale factors in [384, 512)
+    static constexpr bool kScales = true;
+    static constexpr int kPrologueTiles = 8;
+    static __device__ __forceinline__ Acc lowest() { return -INFINITY; }
+    static __device__ __forceinline__ Acc from_bits(uint32_t x) { return __uint_as_float(x); }
+    static __device__ __forceinline__ Acc max3(Acc a, Acc b, Acc c) { return fmaxf(fmaxf(a, b), c); }   // FMNMX3
+    static __device__ __forceinline__ Acc max2(Acc a, Acc b) { return fmaxf(a, b); }
+    static __device__ __forceinline__ bool valid(Acc v) { return v >= -256.0f; }
+    static __device__ __forceinline__ unsigned distance(Acc v) { return (unsigned)((256 - (int)v) >> 1); }
+};
+
+template <class C> __host__ __device__ constexpr int row_block_bytes() { return kRowBlock * C::kRowBytes; }
+template <class C> __host__ __device__ constexpr int a_bytes() { return kMBlocks * row_block_bytes<C>(); }
+template <class C> __host__ __device__ constexpr int b_stage_bytes() { return row_block_bytes<C>(); }
+template <class C> __host__ __device__ constexpr int smem_bytes() { return 1024 + a_bytes<C>() + C::kStages * b_stage_bytes<C>() + 256; }
+static_assert((2 * CoreF4::kStages + 1 + 2 * CoreF4::kUnits) * 8 + 16 <= 256, "barrier block");
+static_assert((2 * CoreI8::kStages + 1 + 2 * CoreI8::kUnits) * 8 + 16 <= 256, "barrier block");
+constexpr int kScaleCol = CoreF4::kUnits * kBlockN;          // first scale-factor column (384)
+
 // ------------------------------------------------------------------------------------------
-// hm_prepare: packed bits -> +/-1 int8 in the tiled swizzled layout.  One thread writes one
-// 16-byte chunk (16 descriptor bits); consecutive threads write consecutive chunks.
+// hm_prepare: packed bits -> +/-1 in the tiled swizzled layout.  One thread writes one 16-byte
+// chunk (16 descriptor bits as int8, 32 as e2m1); consecutive threads write consecutive chunks.
 // ------------------------------------------------------------------------------------------
 struct PrepareParams {
     const uint8_t* bits;
@@ -96,12 +139,44 @@ __global__ void __launch_bounds__(256) hm_prepare_kernel(const PrepareParams P)
     dst[o] = v;
 }
 
+// e2m1 image: one 128-byte slab per row, chunk c = descriptor bytes [4c, 4c+4)
+__global__ void __launch_bounds__(256) hm_prepare_f4_kernel(const PrepareParams P)
+{
+    const long long chunks_per_problem = P.padded_rows * 8;
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= chunks_per_problem) return;
+    const int b = blockIdx.y;
+    const long long rb = o >> 10;            // 1024 chunks per 128-row block
+    const int rem = (int)(o & 1023);
+    const int rr = (rem >> 3) & 7;
+    const int r = ((rem >> 6) << 3) | rr;
+    const int c = (rem & 7) ^ rr;
+    const long long row = rb * kRowBlock + r;
+    uint4 v = make_uint4(0, 0, 0, 0);        // padding rows: +0.0 everywhere
+    if (row < P.n) {
+        const unsigned bits32 = *reinterpret_cast<const unsigned*>(P.bits + (long long)b * P.batch_stride + row * P.stride + c * 4);
+        unsigned w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const unsigned by = (bits32 >> (8 * i)) & 0xFF;
+            // bit j -> bit 4j+3 (the e2m1 sign): set = +1.0 (0x2), clear = -1.0 (0xA)
+            unsigned s = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s |= ((by >> j) & 1u) << (4 * j + 3);
+            w[i] = 0xAAAAAAAAu ^ s;
+        }
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(P.out + (long long)b * P.padded_rows * HM_PREPARED_F4_ROW_BYTES);
+    dst[o] = v;
+}
+
 // ------------------------------------------------------------------------------------------
 // main kernel
 // ------------------------------------------------------------------------------------------
-struct I8Params {
-    const uint8_t* qprep;            // [batch][q_padded][256]
-    const uint8_t* tprep;            // [batch][t_padded][256]
+struct TcParams {
+    const uint8_t* qprep;            // [batch][q_padded][row bytes]
+    const uint8_t* tprep;            // [batch][t_padded][row bytes]
     long long nq, nt;
     long long q_padded, t_padded;
     int tiles_per_split;             // train tiles (128 rows) per split
@@ -120,14 +195,15 @@ struct I8Params {
 
 constexpr int kTraceTiles = 96;
 constexpr int kTraceSlots = 8;
-__device__ __forceinline__ void trace_mark(const I8Params& P, int tile, int slot)
+__device__ __forceinline__ void trace_mark(const TcParams& P, int tile, int slot)
 {
     if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile < kTraceTiles)
         P.trace[tile * kTraceSlots + slot] = clock64();
 }
 
+template <class Acc>
 struct Top2 {
-    int v1, v2;                      // best / second-best dot (larger = closer)
+    Acc v1, v2;                      // best / second-best dot (larger = closer)
     unsigned i1, i2;                 // train row local to this CTA's range
 };
 
@@ -155,24 +231,27 @@ __device__ __forceinline__ void tmem_ld_fence4(uint32_t (&a)[32], uint32_t (&b)[
 // running second best decides whether anything can change the top-2.  Only then are the groups
 // revisited, and the exact (value, index) insertion runs for the groups that still qualify.
 // Strict '>' keeps the lowest train index on ties because columns are visited in ascending order.
-__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], unsigned colbase, unsigned limit, Top2& s)
+template <class C>
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], unsigned colbase, unsigned limit,
+                                           Top2<typename C::Acc>& s)
 {
-    int gm[4];
+    using Acc = typename C::Acc;
+    Acc gm[4];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
         const int o = g * 8;
-        gm[g] = __vimax3_s32(__vimax3_s32((int)r[o], (int)r[o + 1], (int)r[o + 2]),
-                             __vimax3_s32((int)r[o + 3], (int)r[o + 4], (int)r[o + 5]),
-                             max((int)r[o + 6], (int)r[o + 7]));
+        gm[g] = C::max3(C::max3(C::from_bits(r[o]), C::from_bits(r[o + 1]), C::from_bits(r[o + 2])),
+                        C::max3(C::from_bits(r[o + 3]), C::from_bits(r[o + 4]), C::from_bits(r[o + 5])),
+                        C::max2(C::from_bits(r[o + 6]), C::from_bits(r[o + 7])));
     }
-    const int m = __vimax3_s32(gm[0], gm[1], max(gm[2], gm[3]));
+    const Acc m = C::max3(gm[0], gm[1], C::max2(gm[2], gm[3]));
     if (m > s.v2) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
             if (gm[g] > s.v2) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int x = (int)r[g * 8 + e];
+                    const Acc x = C::from_bits(r[g * 8 + e]);
                     const unsigned idx = colbase + g * 8 + e;
                     if (x > s.v2 && idx < limit) {
                         if (x > s.v1) {
@@ -188,21 +267,46 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], unsigned col
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params P)
+// half `h` (0 / 1) of the MMAs of one (tile, query block) item: kSlabs * 2 instructions
+template <class C>
+__device__ __forceinline__ void issue_half(int h, uint32_t a_block, uint32_t b_stage, uint32_t tmem_d, uint32_t idesc,
+                                           uint32_t tmem_sf)
 {
+    constexpr int kHalf = C::kSlabs * 2;
+#pragma unroll
+    for (int jj = 0; jj < kHalf; ++jj) {
+        const int j = h * kHalf + jj;
+        const int slab = j >> 2, k = j & 3;
+        const uint64_t da = ptx::make_kmajor_sw128_desc(a_block + slab * kSlabBytes + k * 32);
+        const uint64_t db = ptx::make_kmajor_sw128_desc(b_stage + slab * kSlabBytes + k * 32);
+        if constexpr (C::kScales) ptx::mma_mxf4_ss(tmem_d, da, db, idesc, tmem_sf, tmem_sf + 64, j != 0);
+        else                      ptx::mma_i8_ss(tmem_d, da, db, idesc, j != 0);
+    }
+}
+
+template <class C>
+__device__ __forceinline__ void tc_knn2_body(const TcParams& P)
+{
+    using Acc = typename C::Acc;
+    constexpr int kStages = C::kStages;
+    constexpr int kUnits = C::kUnits;
+    constexpr int kABytes = a_bytes<C>();
+    constexpr int kBStageBytes = b_stage_bytes<C>();
+    constexpr int kRowBlockBytes = row_block_bytes<C>();
+
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
     uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* smem_a = smem;                      // [query block 0: slab0 | slab1][query block 1: slab0 | slab1]
-    uint8_t* smem_b = smem + kABytes;            // kStages x [slab0 | slab1] of one 128-row train tile
+    uint8_t* smem_a = smem;                      // [query block 0][query block 1], each [slab 0 | slab 1 ...]
+    uint8_t* smem_b = smem + kABytes;            // kStages x one 128-row train tile
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kABytes + kStages * kBStageBytes);
     uint64_t* full_bar = bars;                   // [kStages]  bulk copies landed
     uint64_t* empty_bar = bars + kStages;        // [kStages]  MMAs reading the stage retired
     uint64_t* a_full_bar = bars + 2 * kStages;   // [1]
-    // accumulator units: u = buffer * kMBlocks + query block, 128 TMEM columns each
-    uint64_t* tmem_full_bar = bars + 2 * kStages + 1;                   // [4] unit complete
-    uint64_t* tmem_empty_bar = bars + 2 * kStages + 1 + 2 * kMBlocks;   // [4] unit drained by its epilogue warps
-    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1 + 4 * kMBlocks);
+    // accumulator units of 128 TMEM columns; work item w = 2 * tile + query block uses unit w % kUnits
+    uint64_t* tmem_full_bar = bars + 2 * kStages + 1;      // [kUnits] unit complete
+    uint64_t* tmem_empty_bar = tmem_full_bar + kUnits;     // [kUnits] unit drained by its epilogue warps
+    uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kUnits);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -225,9 +329,9 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
             ptx::mbar_init(&empty_bar[i], cs);           // one (multicast) commit per CTA of the cluster
         }
         ptx::mbar_init(a_full_bar, 1);
-        for (int i = 0; i < 2 * kMBlocks; ++i) {
+        for (int i = 0; i < kUnits; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], 4);       // one arrival per epilogue warp of that query block
+            ptx::mbar_init(&tmem_empty_bar[i], 4);       // one arrival per epilogue warp of the item's query block
         }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -241,15 +345,31 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_base_slot;
 
+    if constexpr (C::kScales) {
+        // every block scale is 1.0 (ue8m0 0x7F): fill the scale-factor columns once, all 128 lanes
+        if (warp >= 2 && warp < 6) {
+            uint32_t ones[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ones[i] = 0x7F7F7F7Fu;
+            const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + kScaleCol;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) ptx::tmem_st_32x32(taddr + c * 32, ones);
+            ptx::tmem_st_wait();
+        }
+        ptx::tc_fence_before();
+        __syncthreads();
+        ptx::tc_fence_after();
+    }
+
     if (warp == 0) {
         // ===== producer: bulk async copies global -> shared =====
         if (lane == 0) {
             if (has_a) {
-                const uint8_t* qsrc = P.qprep + ((long long)b * P.q_padded + (long long)qb * kBlockM) * HM_PREPARED_ROW_BYTES;
+                const uint8_t* qsrc = P.qprep + ((long long)b * P.q_padded + (long long)qb * kBlockM) * C::kRowBytes;
                 ptx::mbar_arrive_expect_tx(a_full_bar, kABytes);
-                ptx::bulk_g2s(smem_a, qsrc, kABytes, a_full_bar);       // two consecutive row blocks, 64 KB
+                ptx::bulk_g2s(smem_a, qsrc, kABytes, a_full_bar);       // two consecutive row blocks
             }
-            const uint8_t* tsrc = P.tprep + (long long)b * P.t_padded * HM_PREPARED_ROW_BYTES;
+            const uint8_t* tsrc = P.tprep + (long long)b * P.t_padded * C::kRowBytes;
             const uint32_t piece = kBStageBytes / cs;     // this CTA fetches 1/cs of every tile and multicasts it
             for (int i = 0; i < my_tiles; ++i) {
                 const int stage = i % kStages;
@@ -272,56 +392,49 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
         // (Two issuer warps were tried: they fall into lockstep on the shared barriers and their gaps
         // coincide -- trace in profiles/r01c_trace_i8_64k.txt.)
         if (ptx::elect_one()) {
-            constexpr uint32_t idesc = ptx::make_i8_idesc(kRowBlock, kBlockN);
+            const uint32_t idesc = C::kScales ? ptx::make_mxf4_idesc(kRowBlock, kBlockN) : ptx::make_i8_idesc(kRowBlock, kBlockN);
             const uint32_t a_addr = ptx::smem_u32(smem_a);
             const uint32_t b_addr = ptx::smem_u32(smem_b);
+            const uint32_t tmem_sf = tmem_base + kScaleCol;
             if (has_a) bounded_wait(a_full_bar, 0, P.error_flag);
-            bool ready0 = false;                          // full[stage] and empty[unit 0] of tile i observed
+            int unit = 0;                                 // unit of the next work item
+            uint32_t upar = 1;                            // parity its "empty" barrier is waited on: (use & 1) ^ 1
+            bool ready0 = false;                          // full[stage] and empty[unit] of tile i's first item observed
             for (int i = 0; i < my_tiles; ++i) {
                 const int stage = i % kStages;
                 const uint32_t use = i / kStages;
-                const int unit0 = (i & 1) * kMBlocks;
-                const uint32_t unit_par = ((uint32_t)(i >> 1) & 1) ^ 1;
                 const uint32_t b_stage = b_addr + stage * kBStageBytes;
+                const int unit_a = unit;
+                const uint32_t par_a = upar;
+                if (++unit == kUnits) { unit = 0; upar ^= 1; }
+                const int unit_b = unit;
+                const uint32_t par_b = upar;
+                if (++unit == kUnits) { unit = 0; upar ^= 1; }
                 trace_mark(P, i, 7);                       // loop top
                 if (!ready0) {
                     bounded_wait(&full_bar[stage], use & 1, P.error_flag);
-                    bounded_wait(&tmem_empty_bar[unit0], unit_par, P.error_flag);
+                    bounded_wait(&tmem_empty_bar[unit_a], par_a, P.error_flag);
                 }
-                trace_mark(P, i, 1);                       // operands landed, unit 0 free
+                trace_mark(P, i, 1);                       // operands landed, first unit free
                 ptx::tc_fence_after();
                 // ---- query block 0 ----
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::mma_i8_ss(tmem_base + unit0 * kBlockN, ptx::make_kmajor_sw128_desc(a_addr + k * 32),
-                                   ptx::make_kmajor_sw128_desc(b_stage + k * 32), idesc, k != 0);
-                const bool ready1 = ptx::mbar_test_wait(&tmem_empty_bar[unit0 + 1], unit_par);
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::mma_i8_ss(tmem_base + unit0 * kBlockN, ptx::make_kmajor_sw128_desc(a_addr + kSlabBytes + k * 32),
-                                   ptx::make_kmajor_sw128_desc(b_stage + kSlabBytes + k * 32), idesc, 1);
-                ptx::tc_commit(&tmem_full_bar[unit0]);     // query block 0's accumulator is ready
+                issue_half<C>(0, a_addr, b_stage, tmem_base + unit_a * kBlockN, idesc, tmem_sf);
+                const bool ready1 = ptx::mbar_test_wait(&tmem_empty_bar[unit_b], par_b);
+                issue_half<C>(1, a_addr, b_stage, tmem_base + unit_a * kBlockN, idesc, tmem_sf);
+                ptx::tc_commit(&tmem_full_bar[unit_a]);    // query block 0's accumulator is ready
                 // ---- query block 1 ----
-                if (!ready1) bounded_wait(&tmem_empty_bar[unit0 + 1], unit_par, P.error_flag);
-                trace_mark(P, i, 6);                       // unit 1 free
+                if (!ready1) bounded_wait(&tmem_empty_bar[unit_b], par_b, P.error_flag);
+                trace_mark(P, i, 6);                       // second unit free
                 ptx::tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::mma_i8_ss(tmem_base + (unit0 + 1) * kBlockN,
-                                   ptx::make_kmajor_sw128_desc(a_addr + kRowBlockBytes + k * 32),
-                                   ptx::make_kmajor_sw128_desc(b_stage + k * 32), idesc, k != 0);
+                issue_half<C>(0, a_addr + kRowBlockBytes, b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
                 ready0 = false;
                 if (i + 1 < my_tiles) {
                     const int n = i + 1;
                     ready0 = ptx::mbar_test_wait(&full_bar[n % kStages], (n / kStages) & 1) &&
-                             ptx::mbar_test_wait(&tmem_empty_bar[(n & 1) * kMBlocks], (((uint32_t)(n >> 1)) & 1) ^ 1);
+                             ptx::mbar_test_wait(&tmem_empty_bar[unit], upar);
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    ptx::mma_i8_ss(tmem_base + (unit0 + 1) * kBlockN,
-                                   ptx::make_kmajor_sw128_desc(a_addr + kRowBlockBytes + kSlabBytes + k * 32),
-                                   ptx::make_kmajor_sw128_desc(b_stage + kSlabBytes + k * 32), idesc, 1);
-                ptx::tc_commit(&tmem_full_bar[unit0 + 1]);
+                issue_half<C>(1, a_addr + kRowBlockBytes, b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
+                ptx::tc_commit(&tmem_full_bar[unit_b]);
                 // smem stage reusable (by every producer of the cluster) once these MMAs retire
                 if (cs > 1) ptx::tc_commit_multicast(&empty_bar[stage], cmask);
                 else        ptx::tc_commit(&empty_bar[stage]);
@@ -333,16 +446,15 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
         const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
         const int mblk = (warp - 2) >> 2;                 // which 128-row query block of the CTA
         const long long row = (long long)qb * kBlockM + mblk * kRowBlock + quarter * 32 + lane;
-        Top2 s;
-        s.v1 = s.v2 = INT_MIN;
+        Top2<Acc> s;
+        s.v1 = s.v2 = C::lowest();
         s.i1 = s.i2 = 0;
         const long long first_row = (long long)tile_begin * kBlockN;
         const unsigned limit = (unsigned)min((long long)my_tiles * kBlockN, P.nt - first_row);
+        int unit = mblk;                                  // (2 * i + mblk) % kUnits
+        uint32_t unit_use = 0;                            // (2 * i + mblk) / kUnits
         for (int i = 0; i < my_tiles; ++i) {
-            const int buf = i & 1;
-            const uint32_t buf_use = i >> 1;
-            const int unit = buf * kMBlocks + mblk;
-            bounded_wait(&tmem_full_bar[unit], buf_use & 1, P.error_flag);
+            bounded_wait(&tmem_full_bar[unit], unit_use & 1, P.error_flag);
             if (warp == 2 && lane == 0) trace_mark(P, i, 3);   // epilogue: accumulator complete
             if (warp == 9 && lane == 0) trace_mark(P, i, 5);
             ptx::tc_fence_after();
@@ -359,17 +471,19 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-            scan_chunk(r0, colbase, limit, s);
-            scan_chunk(r1, colbase + 32, limit, s);
-            scan_chunk(r2, colbase + 64, limit, s);
-            scan_chunk(r3, colbase + 96, limit, s);
+            unit += 2;
+            if (unit >= kUnits) { unit -= kUnits; ++unit_use; }
+            scan_chunk<C>(r0, colbase, limit, s);
+            scan_chunk<C>(r1, colbase + 32, limit, s);
+            scan_chunk<C>(r2, colbase + 64, limit, s);
+            scan_chunk<C>(r3, colbase + 96, limit, s);
             if (warp == 2 && lane == 0) trace_mark(P, i, 4);   // epilogue: buffer released
         }
         if (row < P.nq) {
             const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
             ulonglong2 k;
-            k.x = s.v1 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v1) >> 1) << 32) | (gbase + s.i1);
-            k.y = s.v2 == INT_MIN ? kNoMatch : ((unsigned long long)((256 - s.v2) >> 1) << 32) | (gbase + s.i2);
+            k.x = C::valid(s.v1) ? ((unsigned long long)C::distance(s.v1) << 32) | (gbase + s.i1) : kNoMatch;
+            k.y = C::valid(s.v2) ? ((unsigned long long)C::distance(s.v2) << 32) | (gbase + s.i2) : kNoMatch;
             unsigned long long* out = P.out + (long long)split * P.out_split_stride + ((long long)b * P.nq + row) * 2;
             *reinterpret_cast<ulonglong2*>(out) = k;
         }
@@ -397,7 +511,15 @@ __global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const I8Params 
     }
 }
 
-struct I8Plan {
+__global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const TcParams P) { tc_knn2_body<CoreI8>(P); }
+__global__ void __launch_bounds__(kThreads, 1) hm_f4_knn2_kernel(const TcParams P) { tc_knn2_body<CoreF4>(P); }
+
+using KernelFn = void (*)(const TcParams);
+template <class C> KernelFn kernel_of();
+template <> KernelFn kernel_of<CoreI8>() { return hm_i8_knn2_kernel; }
+template <> KernelFn kernel_of<CoreF4>() { return hm_f4_knn2_kernel; }
+
+struct TcPlan {
     int ntiles, splits, tiles_per_split;
     int cluster;                     // CTAs per cluster (query blocks sharing the B tiles)
     long long qblocks;               // grid.x, rounded up to a multiple of `cluster`
@@ -416,6 +538,7 @@ int cluster_override()
 
 // CTAs that can be co-resident when launched as clusters of `cs` (1 CTA per SM; clusters of 4 cannot
 // use every SM of every GPC).  Queried once per cluster size; falls back to the SM count.
+template <class C>
 int resident_ctas(int cs, int sm_count)
 {
     static int cache[5] = {0, 0, 0, 0, 0};
@@ -425,7 +548,7 @@ int resident_ctas(int cs, int sm_count)
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(cs * 64, 1, 1);
         cfg.blockDim = dim3(kThreads);
-        cfg.dynamicSmemBytes = kSmemBytes;
+        cfg.dynamicSmemBytes = smem_bytes<C>();
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = (unsigned)cs;
@@ -434,8 +557,8 @@ int resident_ctas(int cs, int sm_count)
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaFuncSetAttribute(hm_i8_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes) == cudaSuccess &&
-            cudaOccupancyMaxActiveClusters(&n, hm_i8_knn2_kernel, &cfg) == cudaSuccess && n > 0)
+        if (cudaFuncSetAttribute(kernel_of<C>(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()) == cudaSuccess &&
+            cudaOccupancyMaxActiveClusters(&n, kernel_of<C>(), &cfg) == cudaSuccess && n > 0)
             v = n * cs;
         else
             cudaGetLastError();
@@ -444,19 +567,20 @@ int resident_ctas(int cs, int sm_count)
     return v;
 }
 
-I8Plan plan_i8(long long nq, long long nt, int batch, int sm_count)
+template <class C>
+TcPlan plan_tc(long long nq, long long nt, int batch, int sm_count)
 {
-    I8Plan pl{};
+    TcPlan pl{};
     const long long qb = ceil_div(nq, kBlockM);
     // pairs of query blocks share every train tile through multicast: half the L2 reads, +1.7 % on the
     // power-capped C4 workload (6297 vs 6189 Gpairs/s); clusters of 4 lose SMs to GPC packing (6003)
     pl.cluster = qb >= 2 ? 2 : 1;
     if (cluster_override()) pl.cluster = cluster_override();
     pl.qblocks = ceil_div(qb, pl.cluster) * pl.cluster;
-    sm_count = resident_ctas(pl.cluster, sm_count);
+    sm_count = resident_ctas<C>(pl.cluster, sm_count);
     pl.ntiles = (int)ceil_div(nt, kBlockN);
     const long long items = pl.qblocks * batch;
-    // choose the split count minimising (waves) x (tiles per CTA + fixed prologue worth ~4 tiles)
+    // choose the split count minimising (waves) x (tiles per CTA + fixed prologue worth a few tiles)
     long long best_cost = -1;
     int best = 1;
     const int max_splits = (int)min((long long)pl.ntiles, 4096ll);
@@ -464,7 +588,7 @@ I8Plan plan_i8(long long nq, long long nt, int batch, int sm_count)
         const long long tps = ceil_div(pl.ntiles, s);
         const long long real_s = ceil_div(pl.ntiles, tps);
         const long long waves = ceil_div(items * real_s, sm_count);
-        const long long cost = waves * (tps + 4);
+        const long long cost = waves * (tps + C::kPrologueTiles);
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = s;
@@ -478,63 +602,47 @@ I8Plan plan_i8(long long nq, long long nt, int batch, int sm_count)
 
 long long padded_rows(long long n) { return ceil_div(n, kPadRows) * kPadRows; }
 
-}  // namespace
-
-size_t prepared_bytes(long long n) { return (size_t)padded_rows(n) * HM_PREPARED_ROW_BYTES; }
-
-int launch_prepare(const uint8_t* bits, long long n, long long stride, long long batch_stride, int batch,
-                   void* prepared, cudaStream_t stream)
-{
-    if (n <= 0 || batch <= 0) return HM_OK;
-    PrepareParams P{};
-    P.bits = bits; P.n = n; P.stride = stride; P.batch_stride = batch_stride;
-    P.padded_rows = padded_rows(n);
-    P.out = static_cast<uint8_t*>(prepared);
-    const long long chunks = P.padded_rows * 16;
-    dim3 grid((unsigned)ceil_div(chunks, 256), (unsigned)batch);
-    hm_prepare_kernel<<<grid, 256, 0, stream>>>(P);
-    HM_CUDA_CHECK(cudaGetLastError());
-    return HM_OK;
-}
-
 // workspace layout: [256 B][arrival counters][partials][prepared q][prepared t]
-static size_t i8_partials_bytes(long long nq, long long nt, int batch, int sm_count)
+template <class C>
+size_t partials_bytes(long long nq, long long nt, int batch, int sm_count)
 {
-    const I8Plan pl = plan_i8(nq, nt, batch, sm_count);
+    const TcPlan pl = plan_tc<C>(nq, nt, batch, sm_count);
     return (size_t)pl.splits * batch * nq * 2 * sizeof(unsigned long long);   // also when splits == 1 (partials mode)
 }
 
-size_t i8_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare)
+template <class C>
+size_t workspace_bytes_of(long long nq, long long nt, int batch, int sm_count, bool with_prepare)
 {
-    size_t b = 256 + counters_bytes(plan_i8(nq, nt, batch, sm_count).qblocks * batch) + i8_partials_bytes(nq, nt, batch, sm_count);
+    size_t b = 256 + counters_bytes(plan_tc<C>(nq, nt, batch, sm_count).qblocks * batch) + partials_bytes<C>(nq, nt, batch, sm_count);
     b = (b + 1023) & ~(size_t)1023;
-    if (with_prepare) b += (prepared_bytes(nq) + prepared_bytes(nt)) * batch;
+    if (with_prepare) b += (size_t)(padded_rows(nq) + padded_rows(nt)) * C::kRowBytes * batch;
     return b;
 }
 
-int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
-                            unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
-                            int sm_count, cudaStream_t stream, const unsigned long long** out_partials,
-                            int* out_groups, const ExchangeArgs* exchange)
+template <class C>
+int launch_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
+                    unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
+                    int sm_count, cudaStream_t stream, const unsigned long long** out_partials,
+                    int* out_groups, const ExchangeArgs* exchange)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        HM_CUDA_CHECK(cudaFuncSetAttribute(hm_i8_knn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        HM_CUDA_CHECK(cudaFuncSetAttribute(kernel_of<C>(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()));
         attr_set = true;
     }
-    const I8Plan pl = plan_i8(nq, nt, batch, sm_count);
+    const TcPlan pl = plan_tc<C>(nq, nt, batch, sm_count);
     if ((long long)pl.ntiles * kBlockN > (1ll << 32)) {
         set_error("train set too large for 32-bit trainIdx");
         return HM_ERR_UNSUPPORTED;
     }
     const bool keep_partials = out == nullptr;
     const size_t cbytes = counters_bytes(pl.qblocks * batch);
-    const size_t need = 256 + cbytes + i8_partials_bytes(nq, nt, batch, sm_count);
+    const size_t need = 256 + cbytes + partials_bytes<C>(nq, nt, batch, sm_count);
     if (!ws || ws_bytes < need) {
         set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
         return HM_ERR_WORKSPACE;
     }
-    I8Params P{};
+    TcParams P{};
     P.qprep = static_cast<const uint8_t*>(qprep);
     P.tprep = static_cast<const uint8_t*>(tprep);
     P.nq = nq; P.nt = nt;
@@ -584,7 +692,7 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)pl.qblocks, (unsigned)pl.splits, (unsigned)batch);
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = kSmemBytes;
+    cfg.dynamicSmemBytes = smem_bytes<C>();
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -594,10 +702,10 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     profile_mark(true, stream);
-    cudaError_t le = cudaLaunchKernelEx(&cfg, hm_i8_knn2_kernel, P);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kernel_of<C>(), P);
     profile_mark(false, stream);
     if (le != cudaSuccess) {
-        set_error("cudaLaunchKernelEx(hm_i8_knn2_kernel, cluster %d) failed: %s", pl.cluster, cudaGetErrorString(le));
+        set_error("cudaLaunchKernelEx(tensor-core k-NN kernel, cluster %d) failed: %s", pl.cluster, cudaGetErrorString(le));
         return HM_ERR_CUDA;
     }
     HM_CUDA_CHECK(cudaGetLastError());
@@ -607,8 +715,8 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
         HM_CUDA_CHECK(cudaMemcpy(host, P.trace, sizeof(host), cudaMemcpyDeviceToHost));
         cudaFree(P.trace);
         if (FILE* f = fopen(trace_path, "w")) {
-            fprintf(f, "# tile producer_issue issuer_ready (unused) epi2_full epi2_scanned epi9_full issuer_unit1_free issuer_loop_top (cycles since first stamp); tiles/CTA=%d splits=%d cluster=%d\n",
-                    pl.tiles_per_split, pl.splits, pl.cluster);
+            fprintf(f, "# tile producer_issue issuer_ready (unused) epi2_full epi2_scanned epi9_full issuer_unit1_free issuer_loop_top (cycles since first stamp); tiles/CTA=%d splits=%d cluster=%d core=%s\n",
+                    pl.tiles_per_split, pl.splits, pl.cluster, C::kScales ? "mxf4" : "i8");
             long long t0 = host[0];
             for (int i = 0; i < kTraceTiles; ++i) {
                 fprintf(f, "%d", i);
@@ -621,27 +729,84 @@ int launch_i8_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
     if (keep_partials) {
         if (out_partials) *out_partials = partials;
         if (out_groups) *out_groups = pl.splits;
-        return HM_OK;
     }
     return HM_OK;
 }
 
-int launch_i8_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count,
-                   cudaStream_t stream)
+template <class C>
+int launch_prepare_of(const uint8_t* bits, long long n, long long stride, long long batch_stride, int batch,
+                      void* prepared, cudaStream_t stream)
 {
-    const size_t need = i8_workspace_bytes(p.nq, p.nt, p.batch, sm_count, true);
+    if (n <= 0 || batch <= 0) return HM_OK;
+    PrepareParams P{};
+    P.bits = bits; P.n = n; P.stride = stride; P.batch_stride = batch_stride;
+    P.padded_rows = padded_rows(n);
+    P.out = static_cast<uint8_t*>(prepared);
+    const long long chunks = P.padded_rows * (C::kRowBytes / 16);
+    dim3 grid((unsigned)ceil_div(chunks, 256), (unsigned)batch);
+    if (C::kScales) hm_prepare_f4_kernel<<<grid, 256, 0, stream>>>(P);
+    else            hm_prepare_kernel<<<grid, 256, 0, stream>>>(P);
+    HM_CUDA_CHECK(cudaGetLastError());
+    return HM_OK;
+}
+
+template <class C>
+int launch_knn2_of(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count, cudaStream_t stream)
+{
+    const size_t need = workspace_bytes_of<C>(p.nq, p.nt, p.batch, sm_count, true);
     if (!ws || ws_bytes < need) {
         set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
         return HM_ERR_WORKSPACE;
     }
-    const size_t head = i8_workspace_bytes(p.nq, p.nt, p.batch, sm_count, false);
+    const size_t head = workspace_bytes_of<C>(p.nq, p.nt, p.batch, sm_count, false);
     uint8_t* qprep = static_cast<uint8_t*>(ws) + head;
-    uint8_t* tprep = qprep + prepared_bytes(p.nq) * p.batch;
-    int rc = launch_prepare(p.q, p.nq, p.q_stride, p.q_batch_stride, p.batch, qprep, stream);
+    uint8_t* tprep = qprep + (size_t)padded_rows(p.nq) * C::kRowBytes * p.batch;
+    int rc = launch_prepare_of<C>(p.q, p.nq, p.q_stride, p.q_batch_stride, p.batch, qprep, stream);
     if (rc != HM_OK) return rc;
-    rc = launch_prepare(p.t, p.nt, p.t_stride, p.t_batch_stride, p.batch, tprep, stream);
+    rc = launch_prepare_of<C>(p.t, p.nt, p.t_stride, p.t_batch_stride, p.batch, tprep, stream);
     if (rc != HM_OK) return rc;
-    return launch_i8_knn2_prepared(qprep, p.nq, tprep, p.nt, p.batch, p.train_base, out, ws, head, sm_count, stream);
+    return launch_prepared<C>(qprep, p.nq, tprep, p.nt, p.batch, p.train_base, out, ws, head, sm_count, stream, nullptr,
+                              nullptr, nullptr);
+}
+
+}  // namespace
+
+// ---- core dispatch (variant must be HM_VARIANT_I8 or HM_VARIANT_F4) ---------------------------
+size_t prepared_bytes(long long n, int variant)
+{
+    return (size_t)padded_rows(n) * (variant == HM_VARIANT_F4 ? CoreF4::kRowBytes : CoreI8::kRowBytes);
+}
+
+int launch_prepare(const uint8_t* bits, long long n, long long stride, long long batch_stride, int batch,
+                   void* prepared, int variant, cudaStream_t stream)
+{
+    return variant == HM_VARIANT_F4 ? launch_prepare_of<CoreF4>(bits, n, stride, batch_stride, batch, prepared, stream)
+                                    : launch_prepare_of<CoreI8>(bits, n, stride, batch_stride, batch, prepared, stream);
+}
+
+size_t tc_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare, int variant)
+{
+    return variant == HM_VARIANT_F4 ? workspace_bytes_of<CoreF4>(nq, nt, batch, sm_count, with_prepare)
+                                    : workspace_bytes_of<CoreI8>(nq, nt, batch, sm_count, with_prepare);
+}
+
+int launch_tc_knn2_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
+                            unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
+                            int sm_count, int variant, cudaStream_t stream, const unsigned long long** out_partials,
+                            int* out_groups, const ExchangeArgs* exchange)
+{
+    return variant == HM_VARIANT_F4
+               ? launch_prepared<CoreF4>(qprep, nq, tprep, nt, batch, train_base, out, ws, ws_bytes, sm_count, stream,
+                                         out_partials, out_groups, exchange)
+               : launch_prepared<CoreI8>(qprep, nq, tprep, nt, batch, train_base, out, ws, ws_bytes, sm_count, stream,
+                                         out_partials, out_groups, exchange);
+}
+
+int launch_tc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count, int variant,
+                   cudaStream_t stream)
+{
+    return variant == HM_VARIANT_F4 ? launch_knn2_of<CoreF4>(p, out, ws, ws_bytes, sm_count, stream)
+                                    : launch_knn2_of<CoreI8>(p, out, ws, ws_bytes, sm_count, stream);
 }
 
 }  // namespace hm

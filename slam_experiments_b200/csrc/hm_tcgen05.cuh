@@ -1,5 +1,5 @@
 // Thin inline-PTX wrappers for the sm_100a features the tensor-core variant uses:
-// mbarrier, 1-D bulk async copy (UBLKCP), TMEM allocation, tcgen05.mma kind::i8,
+// mbarrier, 1-D bulk async copy (UBLKCP), TMEM allocation, tcgen05.mma kind::i8 / kind::mxf4,
 // tcgen05.commit, tcgen05.ld.  No CUTLASS: the bit layouts of the shared-memory
 // matrix descriptor and the instruction descriptor are spelled out here.
 #pragma once
@@ -173,6 +173,36 @@ __device__ __forceinline__ void mma_i8_ss(uint32_t tmem_d, uint64_t desc_a, uint
         : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem], block-scaled e2m1 x e2m1 -> fp32 (K = 64 per instruction, one ue8m0
+// scale per 32 elements, read from TMEM at tmem_sfa / tmem_sfb), issued by ONE thread
+__device__ __forceinline__ void mma_mxf4_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+
+// 32 lanes x 32 consecutive 32-bit columns, registers -> TMEM (scale-factor fill)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+        "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+        "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+        "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory"); }
+
 // 32 lanes x 32 consecutive 32-bit columns: thread `lane` gets columns [col, col+32) of its TMEM lane
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 {
@@ -211,6 +241,14 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
 __host__ __device__ constexpr uint32_t make_i8_idesc(int m, int n)
 {
     return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// Instruction descriptor for kind::mxf4 (block-scaled), dense, K = 64:
+//   [4,6) B scale-factor id = 0   [7,10) A format = 1 (e2m1)   [10,13) B format = 1   bit 15 / 16: K-major
+//   [17,23) N >> 3   bit 23 scale format = 1 (ue8m0)   [24,29) M >> 4   [29,31) A scale-factor id = 0
+__host__ __device__ constexpr uint32_t make_mxf4_idesc(int m, int n)
+{
+    return (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | (1u << 23) | ((uint32_t)(m >> 4) << 24);
 }
 
 }  // namespace ptx

@@ -69,9 +69,15 @@ class NativeOps:
     def make_shard(self, train: torch.Tensor):
         """Keep the shard resident; for the tensor-core variant also its prepared image."""
         nt = train.shape[0]
-        use_i8 = self.variant == "i8" or (self.variant == "auto" and nt >= 65536)
-        prepared = nat.prepare(train) if (use_i8 and nt > 0) else None
-        return {"bits": train, "prepared": prepared, "nt": nt, "buf": None, "pbuf": None}
+        tc = self._tensor_core(nt)
+        prepared = nat.prepare(train, variant=tc) if (tc and nt > 0) else None
+        return {"bits": train, "prepared": prepared, "tc": tc, "nt": nt, "buf": None, "pbuf": None}
+
+    def _tensor_core(self, nt: int) -> int:
+        """The tensor-core core a resident shard of ``nt`` rows is prepared for (0 = keep packed bits only)."""
+        if self.variant in ("i8", "f4") or (self.variant == "auto" and nt >= 65536):
+            return nat.tensor_variant(self.variant)
+        return 0
 
     def append_rows(self, shard, rows: np.ndarray):
         """Grow the resident shard by ``rows`` (a new keyframe): amortised-doubling device buffers, one
@@ -91,26 +97,29 @@ class NativeOps:
                 shard["pbuf"] = None
             buf[nt:new_nt].copy_(torch.from_numpy(np.ascontiguousarray(rows, dtype=np.uint8)), non_blocking=False)
             shard["bits"] = buf[:new_nt]
-            use_i8 = shard["prepared"] is not None or self.variant == "i8" or (self.variant == "auto" and new_nt >= 65536)
-            if use_i8:
-                need = nat.prepared_bytes(new_nt) + 512 * nat.PREPARED_ROW_BYTES
+            tc = shard.get("tc") or self._tensor_core(new_nt)
+            if tc:
+                row_bytes = nat.PREPARED_ROW_BYTES[tc]
+                need = nat.prepared_bytes(new_nt, tc) + 512 * row_bytes
                 pbuf = shard.get("pbuf")
                 first = 0                                     # first row whose prepared image must be (re)written
                 if pbuf is None or pbuf.numel() < need:
-                    pbuf = torch.empty(max(need, nat.prepared_bytes(buf.shape[0]) + 512 * nat.PREPARED_ROW_BYTES),
+                    pbuf = torch.empty(max(need, nat.prepared_bytes(buf.shape[0], tc) + 512 * row_bytes),
                                        dtype=torch.uint8, device=self.device)
                     shard["pbuf"] = pbuf
                 elif shard["prepared"] is not None:
                     first = (nt // 128) * 128                 # the partially filled block and everything after it
-                nat.prepare(buf[first:new_nt], out=pbuf[first * nat.PREPARED_ROW_BYTES:])
+                nat.prepare(buf[first:new_nt], out=pbuf[first * row_bytes:], variant=tc)
                 shard["prepared"] = pbuf
+                shard["tc"] = tc
             shard["nt"] = new_nt
         return shard
 
     def local_knn2(self, query: torch.Tensor, shard, train_base: int) -> torch.Tensor:
         if shard["prepared"] is not None and query.shape[0] > 0:
-            qprep = nat.prepare(query)
-            return nat.knn2_keys_prepared(qprep, query.shape[0], shard["prepared"], shard["nt"], train_base)
+            qprep = nat.prepare(query, variant=shard["tc"])
+            return nat.knn2_keys_prepared(qprep, query.shape[0], shard["prepared"], shard["nt"], train_base,
+                                          variant=shard["tc"])
         return nat.knn2_keys(query, shard["bits"], train_base=train_base, variant=self.variant)
 
     def all_gather(self, keys: torch.Tensor, group) -> torch.Tensor:
@@ -155,12 +164,13 @@ class NativeOps:
         nq = query.shape[0]
         if x is None or shard["prepared"] is None or not (0 < nq <= x["max_rows"]):
             return self.gather_merge(self.local_knn2(query, shard, train_base), group)
-        qprep = nat.prepare(query)
+        qprep = nat.prepare(query, variant=shard["tc"])
         x["epoch"] += 1
         if self.exchange_kernel == "in_knn":
             return nat.knn2_prepared_exchange(qprep, nq, shard["prepared"], shard["nt"], train_base, x["world"],
-                                              x["rank"], x["ptrs"], x["max_rows"], x["epoch"])
-        ptr, groups = nat.knn2_partials_prepared(qprep, nq, shard["prepared"], shard["nt"], train_base)
+                                              x["rank"], x["ptrs"], x["max_rows"], x["epoch"], variant=shard["tc"])
+        ptr, groups = nat.knn2_partials_prepared(qprep, nq, shard["prepared"], shard["nt"], train_base,
+                                                 variant=shard["tc"])
         return nat.exchange_merge(ptr, x["world"], x["rank"], x["ptrs"], x["max_rows"], x["epoch"], rows=nq,
                                   groups=groups, device=self.device)
 

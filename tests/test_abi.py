@@ -37,15 +37,23 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_version_and_sizing(lib):
-    assert lib.hm_version() == 1
-    assert lib.hm_prepared_bytes(0) == 0
-    assert lib.hm_prepared_bytes(1) == 256 * 256            # padded to whole 256-row tiles
-    assert lib.hm_prepared_bytes(257) == 512 * 256
-    for v in (0, 1, 2):
+    assert lib.hm_version() == 2
+    I8, F4 = nat.VARIANT_I8, nat.VARIANT_F4
+    assert lib.hm_prepared_bytes(0, I8) == 0
+    assert lib.hm_prepared_bytes(1, I8) == 256 * 256        # padded to whole 256-row tiles
+    assert lib.hm_prepared_bytes(257, I8) == 512 * 256
+    assert lib.hm_prepared_bytes(257, F4) == 512 * 128      # e2m1: half the bytes
+    assert lib.hm_prepared_bytes(257, nat.VARIANT_POPC) == 0   # no prepared form
+    tc = lib.hm_default_tensor_variant()
+    assert tc in (I8, F4)
+    assert lib.hm_prepared_bytes(257, 0) == lib.hm_prepared_bytes(257, tc)
+    for v in (0, 1, 2, 3):
         assert lib.hm_workspace_bytes(2000, 2000, 1, v) > 0
-    assert lib.hm_workspace_bytes(2000, 8192000, 1, 2) >= lib.hm_prepared_bytes(8192000)
+    for v in (I8, F4):
+        assert lib.hm_workspace_bytes(2000, 8192000, 1, v) >= lib.hm_prepared_bytes(8192000, v)
+        assert lib.hm_prepared_workspace_bytes(2000, 8192000, v) > 0
     assert lib.hm_select_variant(200, 200, 1) == nat.VARIANT_POPC
-    assert lib.hm_select_variant(16384, 16384, 1) == nat.VARIANT_I8
+    assert lib.hm_select_variant(16384, 16384, 1) == tc
 
 
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
@@ -56,7 +64,7 @@ def test_compute_fails_loudly_without_gpu(lib):
     rc = lib.hm_knn2(buf.ctypes.data, 4, 32, buf.ctypes.data, 4, 32, 0, out.ctypes.data, 0, None, 0, None)
     assert rc == -5 and b"no CUDA device" in lib.hm_last_error()
     assert lib.hm_merge_top2(out.ctypes.data, 1, 2, out.ctypes.data, None) == -5
-    assert lib.hm_prepare(buf.ctypes.data, 4, 32, buf.ctypes.data, None) == -5
+    assert lib.hm_prepare(buf.ctypes.data, 4, 32, buf.ctypes.data, 2, None) == -5
     h = ctypes.c_void_p()
     assert lib.hm_context_create(ctypes.byref(h)) == -5
     assert lib.hm_device_sm_count() == -5

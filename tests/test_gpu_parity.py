@@ -18,7 +18,7 @@ from oracle import c_oracle as co
 
 pytestmark = pytest.mark.gpu
 cv2 = pytest.importorskip("cv2")
-VARIANTS = ("popc", "i8")
+VARIANTS = ("popc", "i8", "f4")
 
 
 def dev(a):
@@ -170,22 +170,28 @@ def test_merge_top2_kernel_and_shard_split():
     t = rng.integers(0, 3, (5000, 32), dtype=np.uint8)
     full = co.knn2_keys(q, t)
     for cuts in ((0, 5000), (0, 1, 5000), (0, 1234, 1235, 4000, 5000), (0, 2500, 5000)):
-        parts = [nat.knn2_keys(dev(q), dev(t[a:b]), train_base=a, variant="popc" if i % 2 else "i8")
+        parts = [nat.knn2_keys(dev(q), dev(t[a:b]), train_base=a, variant=("popc", "i8", "f4")[i % 3])
                  for i, (a, b) in enumerate(zip(cuts[:-1], cuts[1:]))]
         merged = nat.merge_top2(torch.stack(parts)).cpu().numpy().view(np.uint64)
         assert np.array_equal(merged, full)
 
 
-def test_prepared_operands_resident_database():
+@pytest.mark.parametrize("variant", ("i8", "f4"))
+def test_prepared_operands_resident_database(variant):
     q, t = synth.keyframe_database(16, 500, 300, seed=1)
     qd, td = dev(q), dev(t)
-    tp = nat.prepare(td)
-    assert tp.numel() == nat.prepared_bytes(t.shape[0])
-    got = nat.knn2_keys_prepared(nat.prepare(qd), q.shape[0], tp, t.shape[0], train_base=77)
+    tp = nat.prepare(td, variant=variant)
+    assert tp.numel() == nat.prepared_bytes(t.shape[0], variant)
+    got = nat.knn2_keys_prepared(nat.prepare(qd, variant=variant), q.shape[0], tp, t.shape[0], train_base=77,
+                                 variant=variant)
     assert np.array_equal(got.cpu().numpy().view(np.uint64), co.knn2_keys(q, t, train_base=77))
-    # the prepared image really is the +/-1 expansion: dot == 256 - 2 * hamming
-    img = tp.cpu().numpy().view(np.int8)
-    assert set(np.unique(img[: 128 * 256]).tolist()) <= {-1, 1}
+    # the prepared image really is the +/-1 expansion
+    if variant == "i8":
+        img = tp.cpu().numpy().view(np.int8)
+        assert set(np.unique(img[: 128 * 256]).tolist()) <= {-1, 1}
+    else:   # e2m1 nibbles: +1.0 = 0x2, -1.0 = 0xA
+        img = tp.cpu().numpy()[: 128 * 128]
+        assert set(np.unique(img & 0xF).tolist()) <= {0x2, 0xA} and set(np.unique(img >> 4).tolist()) <= {0x2, 0xA}
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -206,7 +212,7 @@ def test_incremental_keyframe_database(variant):
 def test_host_context_c_abi_only():
     ctx = nat.HostContext()
     rng = np.random.default_rng(2)
-    for nq, nt, v in ((200, 200, "auto"), (1000, 1300, "popc"), (1000, 1300, "i8"), (3, 1, "auto")):
+    for nq, nt, v in ((200, 200, "auto"), (1000, 1300, "popc"), (1000, 1300, "i8"), (1000, 1300, "f4"), (3, 1, "auto")):
         q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
         t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
         assert np.array_equal(ctx.knn2_keys(q, t, v), co.knn2_keys(q, t))
@@ -225,7 +231,7 @@ def test_mid_size_vs_c_oracle(variant):
 def test_full_size_properties():
     """BASELINE-size checks through size-independent properties (the oracle cannot run these).
 
-    64k x 64k sweep point: (1) both variants agree bit-for-bit; (2) planted exact duplicates are
+    64k x 64k sweep point: (1) all three variants agree bit-for-bit; (2) planted exact duplicates are
     found at distance 0 with the lowest index first; (3) permuting train rows permutes trainIdx
     wherever the top-2 distances are tie-free; (4) a random sample of rows equals the oracle."""
     n = 65536
@@ -239,6 +245,8 @@ def test_full_size_properties():
     k_i8 = nat.knn2_keys(qd, td, variant="i8").cpu().numpy().view(np.uint64)
     k_pc = nat.knn2_keys(qd, td, variant="popc").cpu().numpy().view(np.uint64)
     assert np.array_equal(k_i8, k_pc)
+    k_f4 = nat.knn2_keys(qd, td, variant="f4").cpu().numpy().view(np.uint64)
+    assert np.array_equal(k_f4, k_pc)
     idx, dist, _ = nat.split_keys(k_i8)
     assert (dist[planted] == 0).all()
     assert np.array_equal(idx[planted, 0], np.minimum(planted, dup))

@@ -47,7 +47,7 @@ def test_oracle_permutation_equivariance(seed, nq, nt):
 @pytest.mark.gpu
 @settings(max_examples=30, **SETTINGS)
 @given(seed=st.integers(0, 2**31 - 1), nq=st.integers(1, 700), nt=st.integers(1, 1500), hi=st.sampled_from([2, 3, 256]),
-       variant=st.sampled_from(["popc", "i8"]), base=st.sampled_from([0, 1, 123456789]))
+       variant=st.sampled_from(["popc", "i8", "f4"]), base=st.sampled_from([0, 1, 123456789]))
 def test_gpu_random_shapes_vs_oracle(seed, nq, nt, hi, variant, base):
     from slam_experiments_b200 import _native as nat
     rng = np.random.default_rng(seed)
@@ -59,7 +59,7 @@ def test_gpu_random_shapes_vs_oracle(seed, nq, nt, hi, variant, base):
 @pytest.mark.gpu
 @settings(max_examples=12, **SETTINGS)
 @given(seed=st.integers(0, 2**31 - 1), nq=st.integers(1, 400), nt=st.integers(1, 900), batch=st.integers(1, 5),
-       variant=st.sampled_from(["popc", "i8"]), ratio=st.sampled_from([None, 0.7, 0.9]), cross=st.booleans())
+       variant=st.sampled_from(["popc", "i8", "f4"]), ratio=st.sampled_from([None, 0.7, 0.9]), cross=st.booleans())
 def test_gpu_fused_pipeline_random(seed, nq, nt, batch, variant, ratio, cross):
     from slam_experiments_b200 import _native as nat
     rng = np.random.default_rng(seed)

@@ -50,7 +50,7 @@ def run(args):
         check = lambda: np.array_equal(fn().cpu().numpy().view(np.uint64)[:64], c_oracle.knn2_keys(q[:64], t))
         cpu_fn = lambda m: cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q[:m], t, k=2)
         cpu_pairs = lambda m: float(m) * n
-        launches = 4 if variant == "i8" else 2
+        launches = 4 if variant in ("i8", "f4") else 2
         nq_k, nt_k = n, n
     elif wl == "c2":
         frames = synth.frame_sequence(100, 2000)
@@ -77,7 +77,7 @@ def run(args):
         ref = cv2.BFMatcher(cv2.NORM_HAMMING)
         cpu_fn = lambda k: [ref.match(frames[i + 1], frames[i]) for i in range(k)]
         cpu_pairs = lambda k: float(k) * 2000 * 2000
-        launches = 4 if variant == "i8" else 2
+        launches = 4 if variant in ("i8", "f4") else 2
         nq_k, nt_k = 2000, 2000
     else:  # c5
         qs, ts = synth.local_window(32, 10000)
@@ -108,7 +108,7 @@ def run(args):
             from oracle import cv2_ref
             return [cv2_ref.pipeline(qs[i], ts[i], 0.75, True) for i in range(k)]
         cpu_pairs = lambda k: float(k) * 10000 * 10000
-        launches = 9 if variant == "i8" else 5
+        launches = 9 if variant in ("i8", "f4") else 5
         nq_k, nt_k = 10000, 10000
 
     verified = bool(check())
@@ -157,12 +157,13 @@ def run(args):
 
     # the event pair brackets the LAST dominant-kernel launch of the call (the swapped pass for c5)
     kpairs = float(nq_k) * nt_k * (1 if wl == "c3" else nb)
-    if variant == "i8":
+    if variant in ("i8", "f4"):
         ach = kpairs * I8_OPS_PER_PAIR / (kms * 1e-3) / 1e12
-        peak = 2.0 * peaks["bf16_tflops"]
-        roof = {"bound": "tensor", "kernel": "hm_i8_knn2_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+        mult = 2.0 if variant == "i8" else 4.0
+        peak = mult * peaks["bf16_tflops"]
+        roof = {"bound": "tensor", "kernel": f"hm_{variant}_knn2_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "kernel_ms": kms,
-                "note": f"int8 ops (512/pair); peak = 2 x bf16_tflops (burst: kernel timed alone) of {peak_src}"}
+                "note": f"+/-1 multiply-add ops (512/pair); peak = {mult:g} x bf16_tflops (burst: kernel timed alone) of {peak_src}"}
     else:
         ach = kpairs * POPC_PER_PAIR / (kms * 1e-3) / 1e12
         peak = nat.sm_count() * 16 * peaks["sm_max_mhz"] * 1e6 / 1e12

@@ -26,19 +26,20 @@ def main():
         q = torch.from_numpy(synth.uniform(nq, 1)).cuda()
         t = torch.from_numpy(synth.uniform(nt, 2)).cuda()
         row = {"nq": nq, "nt": nt}
-        for v in ("popc", "i8"):
+        for v in ("popc", "i8", "f4"):
             if v == "popc" and nq * nt > 3e9 * 2:
                 continue
             med, best = time_it(lambda: nat.knn2_keys(q, t, variant=v), iters=5 if nq * nt > 1e9 else 20)
             row[v] = {"ms": round(med, 4), "best_ms": round(best, 4), "gpairs": round(nq * nt / med / 1e6, 1)}
         if nt >= 65536:
-            tp = nat.prepare(t)
-            def f():
-                nat.knn2_keys_prepared(nat.prepare(q), nq, tp, nt)
-            med, best = time_it(f, iters=5)
-            row["i8_prepared"] = {"ms": round(med, 4), "gpairs": round(nq * nt / med / 1e6, 1)}
-            med, best = time_it(lambda: nat.prepare(t), iters=5)
-            row["prepare_t_ms"] = round(med, 4)
+            for v in ("i8", "f4"):
+                tp = nat.prepare(t, variant=v)
+                def f():
+                    nat.knn2_keys_prepared(nat.prepare(q, variant=v), nq, tp, nt, variant=v)
+                med, best = time_it(f, iters=5)
+                row[v + "_prepared"] = {"ms": round(med, 4), "gpairs": round(nq * nt / med / 1e6, 1)}
+                med, best = time_it(lambda: nat.prepare(t, variant=v), iters=5)
+                row[v + "_prepare_t_ms"] = round(med, 4)
         print(json.dumps(row), flush=True)
 
 

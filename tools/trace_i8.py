@@ -9,9 +9,9 @@ q = torch.from_numpy(synth.uniform(nq, 1)).cuda()
 t = torch.from_numpy(synth.uniform(nt, 2)).cuda()
 os.environ.pop("HM_I8_TRACE")
 for _ in range(2):
-    nat.knn2_keys(q, t, variant="i8")
+    nat.knn2_keys(q, t, variant=os.environ.get("HM_TRACE_VARIANT", "i8"))
 torch.cuda.synchronize()
 os.environ["HM_I8_TRACE"] = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/trace_i8.txt"
-nat.knn2_keys(q, t, variant="i8")
+nat.knn2_keys(q, t, variant=os.environ.get("HM_TRACE_VARIANT", "i8"))
 torch.cuda.synchronize()
 print(open(os.environ["HM_I8_TRACE"]).read())
