@@ -53,7 +53,7 @@ extern "C" {
 #define HM_PREPARED_ROW_BYTES 256
 #define HM_PREPARED_F4_ROW_BYTES 128
 /* the tensor-core core HM_VARIANT_AUTO resolves to (ncu evidence in DESIGN.md) */
-#define HM_DEFAULT_TENSOR_VARIANT 2
+#define HM_DEFAULT_TENSOR_VARIANT 3
 /* prepared images are padded to whole tiles of this many rows */
 #define HM_PREPARED_TILE_ROWS 256
 

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libhm_matcher.so")
+SO_PATH = os.environ.get("HM_MATCHER_SO") or os.path.join(HERE, "libhm_matcher.so")
 
 HM_OK = 0
 VARIANT_AUTO, VARIANT_POPC, VARIANT_I8, VARIANT_F4 = 0, 1, 2, 3

@@ -53,6 +53,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         build_hmfast(force)
     except Exception as e:  # pragma: no cover - optional accelerator
         print(f"warning: _hmfast not built ({e}); DMatch construction falls back to Python", file=sys.stderr)
+    trace = os.environ.get("HM_BUILD_TRACE") == "1"
+    if trace:          # separate file: load it with HM_MATCHER_SO=<path> (tools/trace_i8.py does)
+        so = os.path.join(HERE, "libhm_matcher_trace.so")
+        force = True
+    else:
+        so = SO
     if not force and not is_stale():
         return SO
     cmd = [
@@ -60,14 +66,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-gencode", "arch=compute_100a,code=sm_100a",
         "--cudart", "static", "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
         "-I", os.path.join(ROOT, "include"), "-I", CSRC,
-        "-o", SO,
+        "-o", so,
     ] + [os.path.join(CSRC, f) for f in SOURCES]
+    if trace:      # pipeline-trace build of the tensor-core kernels
+        cmd.insert(1, "-DHM_TC_TRACE=1")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
         print(" ".join(cmd))
     subprocess.check_call(cmd)
-    return SO
+    return so
 
 
 if __name__ == "__main__":

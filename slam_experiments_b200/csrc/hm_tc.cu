@@ -50,8 +50,8 @@ constexpr int kBlockN = kRowBlock;           // train rows per tile
 constexpr int kSlabBytes = kRowBlock * 128;  // 16 KB: 128 rows x 128 bytes of K
 constexpr int kPadRows = HM_PREPARED_TILE_ROWS;
 constexpr int kTmemCols = 512;
-constexpr int kEpilogueWarps = 4 * kMBlocks; // one per 32 query rows
-constexpr int kThreads = 32 * (2 + kEpilogueWarps);  // warp 0 producer, warp 1 MMA issuer, warps 2..9 epilogue
+// warp 0 producer, warp 1 MMA issuer, then 4 * kMBlocks * kColSplit epilogue warps: one per 32 query rows
+// and per 128 / kColSplit columns of a tile
 constexpr uint32_t kSpinLimit = 1u << 26;
 
 static_assert(kPadRows % kBlockN == 0 && kPadRows % kBlockM == 0, "prepared padding must cover whole tiles");
@@ -63,6 +63,7 @@ struct CoreI8 {
     static constexpr int kRowBytes = HM_PREPARED_ROW_BYTES;  // 256
     static constexpr int kStages = 4;                        // 4 x 32 KB in flight
     static constexpr int kUnits = 4;                         // accumulator units of 128 TMEM columns
+    static constexpr int kColSplit = 1;                      // 8 epilogue warps: the MMA (and the power cap) paces this core
     static constexpr bool kScales = false;
     static constexpr int kPrologueTiles = 4;                 // fixed per-CTA cost in tile times (split planning)
     static __device__ __forceinline__ Acc lowest() { return INT_MIN; }
@@ -79,6 +80,10 @@ struct CoreF4 {
     static constexpr int kRowBytes = HM_PREPARED_F4_ROW_BYTES;  // 128
     static constexpr int kStages = 8;                        // 8 x 16 KB in flight (a tile lasts half as long)
     static constexpr int kUnits = 3;                         // columns [0, 384); scale factors in [384, 512)
+    // 16 epilogue warps, two per (query block, lane quarter), 64 columns each: with 8 the scan is latency
+    // bound (ncu r01j: issue slots 37 %, ALU 46 %, top stalls wait / long scoreboard) at 1087 cycles per
+    // tile while the MMAs need 512
+    static constexpr int kColSplit = 2;
     static constexpr bool kScales = true;
     static constexpr int kPrologueTiles = 8;
     static __device__ __forceinline__ Acc lowest() { return -INFINITY; }
@@ -92,7 +97,11 @@ struct CoreF4 {
 template <class C> __host__ __device__ constexpr int row_block_bytes() { return kRowBlock * C::kRowBytes; }
 template <class C> __host__ __device__ constexpr int a_bytes() { return kMBlocks * row_block_bytes<C>(); }
 template <class C> __host__ __device__ constexpr int b_stage_bytes() { return row_block_bytes<C>(); }
-template <class C> __host__ __device__ constexpr int smem_bytes() { return 1024 + a_bytes<C>() + C::kStages * b_stage_bytes<C>() + 256; }
+template <class C> __host__ __device__ constexpr int epilogue_warps() { return 4 * kMBlocks * C::kColSplit; }
+template <class C> __host__ __device__ constexpr int threads() { return 32 * (2 + epilogue_warps<C>()); }
+// + 256 B of barriers, + 4 KB where the epilogue warps of the upper column halves hand over their keys
+constexpr int kHandoverBytes = kBlockM * 16;
+template <class C> __host__ __device__ constexpr int smem_bytes() { return 1024 + a_bytes<C>() + C::kStages * b_stage_bytes<C>() + 256 + kHandoverBytes; }
 static_assert((2 * CoreF4::kStages + 1 + 2 * CoreF4::kUnits) * 8 + 16 <= 256, "barrier block");
 static_assert((2 * CoreI8::kStages + 1 + 2 * CoreI8::kUnits) * 8 + 16 <= 256, "barrier block");
 constexpr int kScaleCol = CoreF4::kUnits * kBlockN;          // first scale-factor column (384)
@@ -191,14 +200,23 @@ struct TcParams {
     ExchangeArgs xch;                // xch.world > 1: the last CTA also exchanges with the peer GPUs (sharded database)
     long long q_blocks_valid;        // 256-row blocks present in qprep (CTAs beyond it are cluster padding)
     long long* trace;                // development aid (HM_I8_TRACE): per-tile clock64 stamps of CTA 0, else null
+    int trace_first;                 // first tile recorded (HM_TRACE_FIRST)
 };
 
+// Pipeline trace (development aid): built only with -DHM_TC_TRACE=1 (HM_BUILD_TRACE=1 python -m
+// slam_experiments_b200.build --force), so the shipped kernels carry no trace instructions.
+#ifndef HM_TC_TRACE
+#define HM_TC_TRACE 0
+#endif
 constexpr int kTraceTiles = 96;
 constexpr int kTraceSlots = 8;
 __device__ __forceinline__ void trace_mark(const TcParams& P, int tile, int slot)
 {
-    if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile < kTraceTiles)
+#if HM_TC_TRACE
+    tile -= P.trace_first;
+    if (P.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tile >= 0 && tile < kTraceTiles)
         P.trace[tile * kTraceSlots + slot] = clock64();
+#endif
 }
 
 template <class Acc>
@@ -224,6 +242,10 @@ __device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity, int
 __device__ __forceinline__ void tmem_ld_fence4(uint32_t (&a)[32], uint32_t (&b)[32], uint32_t (&c)[32], uint32_t (&d)[32])
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(a), HM_R32(b), HM_R32(c), HM_R32(d) : : "memory");
+}
+__device__ __forceinline__ void tmem_ld_fence2(uint32_t (&a)[32], uint32_t (&b)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(a), HM_R32(b) : : "memory");
 }
 
 // 32 consecutive train columns of one query row.  Fast path: 3-input-max trees give the maximum
@@ -307,6 +329,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     uint64_t* tmem_full_bar = bars + 2 * kStages + 1;      // [kUnits] unit complete
     uint64_t* tmem_empty_bar = tmem_full_bar + kUnits;     // [kUnits] unit drained by its epilogue warps
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kUnits);
+    ulonglong2* handover = reinterpret_cast<ulonglong2*>(smem + kABytes + kStages * kBStageBytes + 256);   // [kBlockM]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -331,7 +354,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         ptx::mbar_init(a_full_bar, 1);
         for (int i = 0; i < kUnits; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], 4);       // one arrival per epilogue warp of the item's query block
+            ptx::mbar_init(&tmem_empty_bar[i], 4 * C::kColSplit);   // one arrival per epilogue warp of the item's query block
         }
         ptx::fence_barrier_init();
         ptx::fence_proxy_async();
@@ -360,6 +383,10 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         __syncthreads();
         ptx::tc_fence_after();
     }
+
+    ulonglong2 my_keys = make_ulonglong2(kNoMatch, kNoMatch);   // epilogue threads: top-2 keys of their row (and column half)
+    long long my_row = -1;                                      // >= 0: this thread writes the row's keys
+    int my_row_in_cta = 0;
 
     if (warp == 0) {
         // ===== producer: bulk async copies global -> shared =====
@@ -443,9 +470,12 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         __syncwarp();
     } else {
         // ===== epilogue: TMEM -> registers, running top-2 per query row =====
+        constexpr int kCols = kBlockN / C::kColSplit;     // train columns of a tile this warp scans
         const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
-        const int mblk = (warp - 2) >> 2;                 // which 128-row query block of the CTA
-        const long long row = (long long)qb * kBlockM + mblk * kRowBlock + quarter * 32 + lane;
+        const int mblk = ((warp - 2) >> 2) & 1;           // which 128-row query block of the CTA
+        const int half = (warp - 2) >> 3;                 // which column range of every tile (0 when kColSplit == 1)
+        const int row_in_cta = mblk * kRowBlock + quarter * 32 + lane;
+        const long long row = (long long)qb * kBlockM + row_in_cta;
         Top2<Acc> s;
         s.v1 = s.v2 = C::lowest();
         s.i1 = s.i2 = 0;
@@ -458,35 +488,43 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             if (warp == 2 && lane == 0) trace_mark(P, i, 3);   // epilogue: accumulator complete
             if (warp == 9 && lane == 0) trace_mark(P, i, 5);
             ptx::tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + unit * kBlockN;
-            const unsigned colbase = (unsigned)i * kBlockN;
-            // all four 32-column loads are issued before the first scan so their latencies overlap
-            uint32_t r0[32], r1[32], r2[32], r3[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + unit * kBlockN + half * kCols;
+            const unsigned colbase = (unsigned)i * kBlockN + half * kCols;
+            // all 32-column loads are issued before the first scan so their latencies overlap
+            uint32_t r0[32], r1[32];
             ptx::tmem_ld_32x32(taddr, r0);
             ptx::tmem_ld_32x32(taddr + 32, r1);
-            ptx::tmem_ld_32x32(taddr + 64, r2);
-            ptx::tmem_ld_32x32(taddr + 96, r3);
-            tmem_ld_fence4(r0, r1, r2, r3);
-            // the accumulator unit is in registers: release it before the scan
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
+            if constexpr (C::kColSplit == 1) {
+                uint32_t r2[32], r3[32];
+                ptx::tmem_ld_32x32(taddr + 64, r2);
+                ptx::tmem_ld_32x32(taddr + 96, r3);
+                tmem_ld_fence4(r0, r1, r2, r3);
+                // the accumulator unit is in registers: release it before the scan
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
+                scan_chunk<C>(r0, colbase, limit, s);
+                scan_chunk<C>(r1, colbase + 32, limit, s);
+                scan_chunk<C>(r2, colbase + 64, limit, s);
+                scan_chunk<C>(r3, colbase + 96, limit, s);
+            } else {
+                tmem_ld_fence2(r0, r1);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
+                scan_chunk<C>(r0, colbase, limit, s);
+                scan_chunk<C>(r1, colbase + 32, limit, s);
+            }
             unit += 2;
             if (unit >= kUnits) { unit -= kUnits; ++unit_use; }
-            scan_chunk<C>(r0, colbase, limit, s);
-            scan_chunk<C>(r1, colbase + 32, limit, s);
-            scan_chunk<C>(r2, colbase + 64, limit, s);
-            scan_chunk<C>(r3, colbase + 96, limit, s);
             if (warp == 2 && lane == 0) trace_mark(P, i, 4);   // epilogue: buffer released
         }
-        if (row < P.nq) {
-            const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
-            ulonglong2 k;
-            k.x = C::valid(s.v1) ? ((unsigned long long)C::distance(s.v1) << 32) | (gbase + s.i1) : kNoMatch;
-            k.y = C::valid(s.v2) ? ((unsigned long long)C::distance(s.v2) << 32) | (gbase + s.i2) : kNoMatch;
-            unsigned long long* out = P.out + (long long)split * P.out_split_stride + ((long long)b * P.nq + row) * 2;
-            *reinterpret_cast<ulonglong2*>(out) = k;
-        }
+        const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
+        my_keys.x = C::valid(s.v1) ? ((unsigned long long)C::distance(s.v1) << 32) | (gbase + s.i1) : kNoMatch;
+        my_keys.y = C::valid(s.v2) ? ((unsigned long long)C::distance(s.v2) << 32) | (gbase + s.i2) : kNoMatch;
+        if (half == 1) handover[row_in_cta] = my_keys;    // merged by the warp of the lower column half below
+        else my_row = row;
+        my_row_in_cta = row_in_cta;
     }
 
     ptx::tc_fence_before();
@@ -495,6 +533,15 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
+    }
+    if (my_row >= 0 && my_row < P.nq) {
+        if constexpr (C::kColSplit == 2) {     // fold the upper column half's candidates (u64 min = cv2's order)
+            const ulonglong2 o = handover[my_row_in_cta];
+            top2_insert(my_keys.x, my_keys.y, o.x);
+            top2_insert(my_keys.x, my_keys.y, o.y);
+        }
+        unsigned long long* out = P.out + (long long)split * P.out_split_stride + ((long long)b * P.nq + my_row) * 2;
+        *reinterpret_cast<ulonglong2*>(out) = my_keys;
     }
     // ---- in-kernel merge of the train splits: the last CTA of this query block folds all partials ----
     if (P.counters) {
@@ -511,8 +558,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) hm_i8_knn2_kernel(const TcParams P) { tc_knn2_body<CoreI8>(P); }
-__global__ void __launch_bounds__(kThreads, 1) hm_f4_knn2_kernel(const TcParams P) { tc_knn2_body<CoreF4>(P); }
+__global__ void __launch_bounds__(threads<CoreI8>(), 1) hm_i8_knn2_kernel(const TcParams P) { tc_knn2_body<CoreI8>(P); }
+__global__ void __launch_bounds__(threads<CoreF4>(), 1) hm_f4_knn2_kernel(const TcParams P) { tc_knn2_body<CoreF4>(P); }
 
 using KernelFn = void (*)(const TcParams);
 template <class C> KernelFn kernel_of();
@@ -547,7 +594,7 @@ int resident_ctas(int cs, int sm_count)
     if (cs > 1) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(cs * 64, 1, 1);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(threads<C>());
         cfg.dynamicSmemBytes = smem_bytes<C>();
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -655,6 +702,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
     P.q_blocks_valid = P.q_padded / kBlockM;
     const char* trace_path = getenv("HM_I8_TRACE");
     if (trace_path) {
+        if (const char* tf = getenv("HM_TRACE_FIRST")) P.trace_first = atoi(tf);
         HM_CUDA_CHECK(cudaMalloc(&P.trace, sizeof(long long) * kTraceTiles * kTraceSlots));
         HM_CUDA_CHECK(cudaMemset(P.trace, 0, sizeof(long long) * kTraceTiles * kTraceSlots));
     }
@@ -691,7 +739,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
     }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)pl.qblocks, (unsigned)pl.splits, (unsigned)batch);
-    cfg.blockDim = dim3(kThreads);
+    cfg.blockDim = dim3(threads<C>());
     cfg.dynamicSmemBytes = smem_bytes<C>();
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -719,7 +767,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
                     pl.tiles_per_split, pl.splits, pl.cluster, C::kScales ? "mxf4" : "i8");
             long long t0 = host[0];
             for (int i = 0; i < kTraceTiles; ++i) {
-                fprintf(f, "%d", i);
+                fprintf(f, "%d", i + P.trace_first);
                 for (int k = 0; k < 8; ++k) fprintf(f, " %lld", host[i * kTraceSlots + k] ? host[i * kTraceSlots + k] - t0 : -1);
                 fprintf(f, "\n");
             }

@@ -22,11 +22,11 @@ def main():
     cat = np.concatenate(kfs)
     lo, hi, _, _ = sx.shard_ranges(sizes, world)[rank]
     ok = True
-    for mode in ("fused", "nccl"):
+    for mode, variant in (("fused", "f4"), ("fused", "i8"), ("fused", "popc"), ("nccl", "f4"), ("nccl", "auto")):
         db = sx.ShardedKeyframeDatabase(sizes, kfs[lo:hi], rank=rank, world_size=world, group=dist.group.WORLD,
-                                        exchange=mode, variant="auto")
+                                        exchange=mode, variant=variant)
         if rank == 0:
-            print(f"mode {mode}: exchange_mode={db.exchange_mode}", flush=True)
+            print(f"mode {mode} variant {variant}: exchange_mode={db.exchange_mode}", flush=True)
         for it, nq in enumerate((700, 1, 2000, 333, 4096, 129, 700)):
             q = rng.integers(0, 3, (nq, 32), dtype=np.uint8)
             q[: min(nq, 7)] = kfs[2][: min(nq, 7)]
@@ -35,7 +35,7 @@ def main():
             good = np.array_equal(keys, exp)
             ok &= good
             if not good:
-                print(f"rank {rank} mode {mode} call {it} nq {nq}: MISMATCH", flush=True)
+                print(f"rank {rank} mode {mode} variant {variant} call {it} nq {nq}: MISMATCH", flush=True)
         rows = db.knnMatch(q, 2)
         ok &= rows[0][0].imgIdx == 2 and rows[0][0].trainIdx == 0 and rows[0][1].imgIdx == 30
     t = torch.tensor([int(ok)], device="cuda")
