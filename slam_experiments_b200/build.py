@@ -69,7 +69,11 @@ def build(force: bool = False, verbose: bool = False) -> str:
         "-o", so,
     ] + [os.path.join(CSRC, f) for f in SOURCES]
     if trace:      # pipeline-trace build of the tensor-core kernels
-        cmd.insert(1, "-DHM_TC_TRACE=1")
+        cmd.insert(1, "-DHM_TC_TRACE=" + os.environ.get("HM_BUILD_TRACE_STAMPS", "1"))
+        if os.environ.get("HM_BUILD_EXPERIMENT"):
+            cmd.insert(1, "-DHM_TC_EXPERIMENT=" + os.environ["HM_BUILD_EXPERIMENT"])
+            so = os.path.join(HERE, f"libhm_matcher_exp{os.environ['HM_BUILD_EXPERIMENT']}.so")
+            cmd[cmd.index("-o") + 1] = so
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

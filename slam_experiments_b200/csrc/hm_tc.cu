@@ -208,6 +208,11 @@ struct TcParams {
 #ifndef HM_TC_TRACE
 #define HM_TC_TRACE 0
 #endif
+// timing experiments (WRONG RESULTS, development builds only): 1 = epilogue loads and releases the
+// accumulators but does not scan them, 2 = epilogue releases without loading
+#ifndef HM_TC_EXPERIMENT
+#define HM_TC_EXPERIMENT 0
+#endif
 constexpr int kTraceTiles = 96;
 constexpr int kTraceSlots = 8;
 __device__ __forceinline__ void trace_mark(const TcParams& P, int tile, int slot)
@@ -331,7 +336,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kUnits);
     ulonglong2* handover = reinterpret_cast<ulonglong2*>(smem + kABytes + kStages * kBStageBytes + 256);   // [kBlockM]
 
-    const int warp = threadIdx.x >> 5;
+    // broadcast from lane 0: lets ptxas treat the warp index (and the role branches on it) as warp-uniform
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
     const int qb = blockIdx.x;                   // 256-row query block
     const int split = blockIdx.y;
@@ -411,55 +417,63 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer: ONE thread runs the whole issue loop =====
+        // ===== MMA issuer =====
         // tcgen05.mma issue blocks while the tensor-core queue is full, so every barrier round trip
         // (~100-150 cycles) taken between two groups of MMAs is a bubble in the tensor pipe.  The
         // barriers of the NEXT group are therefore probed (mbarrier.test_wait, non-blocking) in the
         // middle of the current group, while its MMAs execute; the blocking wait is only the fallback.
-        // (Two issuer warps were tried: they fall into lockstep on the shared barriers and their gaps
-        // coincide -- trace in profiles/r01c_trace_i8_64k.txt.)
-        if (ptx::elect_one()) {
-            const uint32_t idesc = C::kScales ? ptx::make_mxf4_idesc(kRowBlock, kBlockN) : ptx::make_i8_idesc(kRowBlock, kBlockN);
-            const uint32_t a_addr = ptx::smem_u32(smem_a);
-            const uint32_t b_addr = ptx::smem_u32(smem_b);
-            const uint32_t tmem_sf = tmem_base + kScaleCol;
-            if (has_a) bounded_wait(a_full_bar, 0, P.error_flag);
-            int unit = 0;                                 // unit of the next work item
-            uint32_t upar = 1;                            // parity its "empty" barrier is waited on: (use & 1) ^ 1
-            bool ready0 = false;                          // full[stage] and empty[unit] of tile i's first item observed
-            for (int i = 0; i < my_tiles; ++i) {
-                const int stage = i % kStages;
-                const uint32_t use = i / kStages;
-                const uint32_t b_stage = b_addr + stage * kBStageBytes;
-                const int unit_a = unit;
-                const uint32_t par_a = upar;
-                if (++unit == kUnits) { unit = 0; upar ^= 1; }
-                const int unit_b = unit;
-                const uint32_t par_b = upar;
-                if (++unit == kUnits) { unit = 0; upar ^= 1; }
-                trace_mark(P, i, 7);                       // loop top
-                if (!ready0) {
-                    bounded_wait(&full_bar[stage], use & 1, P.error_flag);
-                    bounded_wait(&tmem_empty_bar[unit_a], par_a, P.error_flag);
-                }
-                trace_mark(P, i, 1);                       // operands landed, first unit free
-                ptx::tc_fence_after();
-                // ---- query block 0 ----
-                issue_half<C>(0, a_addr, b_stage, tmem_base + unit_a * kBlockN, idesc, tmem_sf);
-                const bool ready1 = ptx::mbar_test_wait(&tmem_empty_bar[unit_b], par_b);
+        // The whole warp runs the loop so that counters, stage / unit indices, barrier addresses and the
+        // shared-memory descriptors stay in the uniform datapath; only the tcgen05 instructions are
+        // predicated on the elected lane.  (With the loop inside `if (elect_one())` every operand went
+        // through a vector register and an R2UR: ~140 dependent instructions of one thread per tile, which
+        // paced the kind::mxf4 core at 114 cycles per MMA instead of 64 -- profiles/r01k_trace_f4_c4_tiles1200.txt.
+        // Two issuer warps were tried before: they fall into lockstep on the shared barriers and their
+        // gaps coincide -- profiles/r01c_trace_i8_64k.txt.)
+        const bool leader = ptx::elect_one();
+        const uint32_t idesc = C::kScales ? ptx::make_mxf4_idesc(kRowBlock, kBlockN) : ptx::make_i8_idesc(kRowBlock, kBlockN);
+        const uint32_t a_addr = ptx::smem_u32(smem_a);
+        const uint32_t b_addr = ptx::smem_u32(smem_b);
+        const uint32_t tmem_sf = tmem_base + kScaleCol;
+        if (has_a) bounded_wait(a_full_bar, 0, P.error_flag);
+        int unit = 0;                                 // unit of the next work item
+        uint32_t upar = 1;                            // parity its "empty" barrier is waited on: (use & 1) ^ 1
+        bool ready0 = false;                          // full[stage] and empty[unit] of tile i's first item observed
+        for (int i = 0; i < my_tiles; ++i) {
+            const int stage = i % kStages;
+            const uint32_t use = i / kStages;
+            const uint32_t b_stage = b_addr + stage * kBStageBytes;
+            const int unit_a = unit;
+            const uint32_t par_a = upar;
+            if (++unit == kUnits) { unit = 0; upar ^= 1; }
+            const int unit_b = unit;
+            const uint32_t par_b = upar;
+            if (++unit == kUnits) { unit = 0; upar ^= 1; }
+            if (leader) trace_mark(P, i, 7);           // loop top
+            if (!ready0) {
+                bounded_wait(&full_bar[stage], use & 1, P.error_flag);
+                bounded_wait(&tmem_empty_bar[unit_a], par_a, P.error_flag);
+            }
+            if (leader) trace_mark(P, i, 1);           // operands landed, first unit free
+            ptx::tc_fence_after();
+            // ---- query block 0 ----
+            if (leader) issue_half<C>(0, a_addr, b_stage, tmem_base + unit_a * kBlockN, idesc, tmem_sf);
+            const bool ready1 = __all_sync(0xffffffffu, ptx::mbar_test_wait(&tmem_empty_bar[unit_b], par_b));
+            if (leader) {
                 issue_half<C>(1, a_addr, b_stage, tmem_base + unit_a * kBlockN, idesc, tmem_sf);
                 ptx::tc_commit(&tmem_full_bar[unit_a]);    // query block 0's accumulator is ready
-                // ---- query block 1 ----
-                if (!ready1) bounded_wait(&tmem_empty_bar[unit_b], par_b, P.error_flag);
-                trace_mark(P, i, 6);                       // second unit free
-                ptx::tc_fence_after();
-                issue_half<C>(0, a_addr + kRowBlockBytes, b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
-                ready0 = false;
-                if (i + 1 < my_tiles) {
-                    const int n = i + 1;
-                    ready0 = ptx::mbar_test_wait(&full_bar[n % kStages], (n / kStages) & 1) &&
-                             ptx::mbar_test_wait(&tmem_empty_bar[unit], upar);
-                }
+            }
+            // ---- query block 1 ----
+            if (!ready1) bounded_wait(&tmem_empty_bar[unit_b], par_b, P.error_flag);
+            if (leader) trace_mark(P, i, 6);           // second unit free
+            ptx::tc_fence_after();
+            if (leader) issue_half<C>(0, a_addr + kRowBlockBytes, b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
+            ready0 = false;
+            if (i + 1 < my_tiles) {
+                const int n = i + 1;
+                ready0 = __all_sync(0xffffffffu, ptx::mbar_test_wait(&full_bar[n % kStages], (n / kStages) & 1) &&
+                                                     ptx::mbar_test_wait(&tmem_empty_bar[unit], upar));
+            }
+            if (leader) {
                 issue_half<C>(1, a_addr + kRowBlockBytes, b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
                 ptx::tc_commit(&tmem_full_bar[unit_b]);
                 // smem stage reusable (by every producer of the cluster) once these MMAs retire
@@ -492,8 +506,10 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             const unsigned colbase = (unsigned)i * kBlockN + half * kCols;
             // all 32-column loads are issued before the first scan so their latencies overlap
             uint32_t r0[32], r1[32];
+#if HM_TC_EXPERIMENT != 2
             ptx::tmem_ld_32x32(taddr, r0);
             ptx::tmem_ld_32x32(taddr + 32, r1);
+#endif
             if constexpr (C::kColSplit == 1) {
                 uint32_t r2[32], r3[32];
                 ptx::tmem_ld_32x32(taddr + 64, r2);
@@ -508,12 +524,22 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 scan_chunk<C>(r2, colbase + 64, limit, s);
                 scan_chunk<C>(r3, colbase + 96, limit, s);
             } else {
+#if HM_TC_EXPERIMENT == 2
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
+#else
                 tmem_ld_fence2(r0, r1);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
+#if HM_TC_EXPERIMENT == 1
+                if (r0[lane] == 0x12345678u && r1[lane] == 0x9abcdef0u) s.i1 = colbase;   // keep the loads alive
+#else
                 scan_chunk<C>(r0, colbase, limit, s);
                 scan_chunk<C>(r1, colbase + 32, limit, s);
+#endif
+#endif
             }
             unit += 2;
             if (unit >= kUnits) { unit -= kUnits; ++unit_use; }
