@@ -427,8 +427,13 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         // predicated on the elected lane.  (With the loop inside `if (elect_one())` every operand went
         // through a vector register and an R2UR: ~140 dependent instructions of one thread per tile, which
         // paced the kind::mxf4 core at 114 cycles per MMA instead of 64 -- profiles/r01k_trace_f4_c4_tiles1200.txt.
-        // Two issuer warps were tried before: they fall into lockstep on the shared barriers and their
-        // gaps coincide -- profiles/r01c_trace_i8_64k.txt.)
+        // Two issuer warps (one per query block, per-(unit, block) barriers, stage released by an epilogue
+        // thread) were tried twice: with the epilogue switched off they lower the floor from 622 to 557
+        // cycles per tile, but with the real epilogue the kind::mxf4 core is slower (860-880 vs 803): the
+        // items of both blocks then complete together, and three accumulator units cannot hide the
+        // drain latency.  Also measured: an epilogue-driven stage release through
+        // mbarrier.arrive.release.cluster costs the arriving thread ~2000 cycles per call (relaxed: none),
+        // and blocking waits instead of the probes cost 70 cycles per tile.)
         const bool leader = ptx::elect_one();
         const uint32_t idesc = C::kScales ? ptx::make_mxf4_idesc(kRowBlock, kBlockN) : ptx::make_i8_idesc(kRowBlock, kBlockN);
         const uint32_t a_addr = ptx::smem_u32(smem_a);
