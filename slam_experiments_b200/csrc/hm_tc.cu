@@ -248,9 +248,9 @@ __device__ __forceinline__ void tmem_ld_fence4(uint32_t (&a)[32], uint32_t (&b)[
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(a), HM_R32(b), HM_R32(c), HM_R32(d) : : "memory");
 }
-__device__ __forceinline__ void tmem_ld_fence2(uint32_t (&a)[32], uint32_t (&b)[32])
+__device__ __forceinline__ void tmem_ld_fence64(uint32_t (&a)[64])
 {
-    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(a), HM_R32(b) : : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R8(a, 0), HM_R8(a, 8), HM_R8(a, 16), HM_R8(a, 24), HM_R8(a, 32), HM_R8(a, 40), HM_R8(a, 48), HM_R8(a, 56) : : "memory");
 }
 
 // 32 consecutive train columns of one query row.  Fast path: 3-input-max trees give the maximum
@@ -259,7 +259,7 @@ __device__ __forceinline__ void tmem_ld_fence2(uint32_t (&a)[32], uint32_t (&b)[
 // revisited, and the exact (value, index) insertion runs for the groups that still qualify.
 // Strict '>' keeps the lowest train index on ties because columns are visited in ascending order.
 template <class C>
-__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], unsigned colbase, unsigned limit,
+__device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, unsigned limit,
                                            Top2<typename C::Acc>& s)
 {
     using Acc = typename C::Acc;
@@ -509,14 +509,11 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             ptx::tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + unit * kBlockN + half * kCols;
             const unsigned colbase = (unsigned)i * kBlockN + half * kCols;
-            // all 32-column loads are issued before the first scan so their latencies overlap
-            uint32_t r0[32], r1[32];
-#if HM_TC_EXPERIMENT != 2
-            ptx::tmem_ld_32x32(taddr, r0);
-            ptx::tmem_ld_32x32(taddr + 32, r1);
-#endif
             if constexpr (C::kColSplit == 1) {
-                uint32_t r2[32], r3[32];
+                // all four 32-column loads are issued before the first scan so their latencies overlap
+                uint32_t r0[32], r1[32], r2[32], r3[32];
+                ptx::tmem_ld_32x32(taddr, r0);
+                ptx::tmem_ld_32x32(taddr + 32, r1);
                 ptx::tmem_ld_32x32(taddr + 64, r2);
                 ptx::tmem_ld_32x32(taddr + 96, r3);
                 tmem_ld_fence4(r0, r1, r2, r3);
@@ -529,20 +526,23 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 scan_chunk<C>(r2, colbase + 64, limit, s);
                 scan_chunk<C>(r3, colbase + 96, limit, s);
             } else {
+                uint32_t r[64];
 #if HM_TC_EXPERIMENT == 2
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
 #else
-                tmem_ld_fence2(r0, r1);
+                ptx::tmem_ld_32x64(taddr, r);
+                tmem_ld_fence64(r);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
 #if HM_TC_EXPERIMENT == 1
-                if (r0[lane] == 0x12345678u && r1[lane] == 0x9abcdef0u) s.i1 = colbase;   // keep the loads alive
+                if (r[lane] == 0x12345678u && r[32 + lane] == 0x9abcdef0u) s.i1 = colbase;   // keep the loads alive
 #else
-                scan_chunk<C>(r0, colbase, limit, s);
-                scan_chunk<C>(r1, colbase + 32, limit, s);
+                // (one flat 64-column tree with a single branch was tried: 867 instead of 795 cycles per tile)
+                scan_chunk<C>(r, colbase, limit, s);
+                scan_chunk<C>(r + 32, colbase + 32, limit, s);
 #endif
 #endif
             }
