@@ -374,9 +374,9 @@ def run_b200(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * 32, "d2h_bytes_per_step": NQ * 16,
                 "ms_per_step": e2e_s * 1e3, "api": "ShardedKeyframeDatabase.knnMatch(query_numpy, 2) -> DMatch tuples",
                 "arrays_out_ms_per_step": e2e_arr_s * 1e3},
-        # per step: prepare(query) + k-NN + split merge, plus (N>1) the fused exchange kernel, or the merge
-        # kernel after NCCL's all-gather
-        "gpu_launches": args.steps * (3 if world == 1 or db.exchange_mode == "fused" else 4),
+        # per step: hm_prepare*_kernel (query expansion) + the k-NN kernel (split merge and, for N > 1, the fused
+        # exchange run inside it); with the NCCL exchange one hm_merge_top2_kernel more (ncu launch list in profiles/)
+        "gpu_launches": args.steps * (2 if world == 1 or db.exchange_mode == "fused" else 3),
         "roofline": roofline,
         "verified_vs_oracle": verified,
     }

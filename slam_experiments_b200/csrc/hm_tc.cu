@@ -72,6 +72,8 @@ struct CoreI8 {
     static __device__ __forceinline__ Acc max2(Acc a, Acc b) { return max(a, b); }
     static __device__ __forceinline__ bool valid(Acc v) { return v != INT_MIN; }
     static __device__ __forceinline__ unsigned distance(Acc v) { return (unsigned)((256 - v) >> 1); }
+    static __device__ __forceinline__ unsigned encode(Acc v) { return (unsigned)(v + 257); }          // 1..513, 0 = none
+    static __device__ __forceinline__ Acc floor_from(unsigned e) { return (int)e - 259; }             // dot - 2
 };
 
 struct CoreF4 {
@@ -92,6 +94,8 @@ struct CoreF4 {
     static __device__ __forceinline__ Acc max2(Acc a, Acc b) { return fmaxf(a, b); }
     static __device__ __forceinline__ bool valid(Acc v) { return v >= -256.0f; }
     static __device__ __forceinline__ unsigned distance(Acc v) { return (unsigned)((256 - (int)v) >> 1); }
+    static __device__ __forceinline__ unsigned encode(Acc v) { return (unsigned)((int)v + 257); }
+    static __device__ __forceinline__ Acc floor_from(unsigned e) { return (float)((int)e - 259); }
 };
 
 template <class C> __host__ __device__ constexpr int row_block_bytes() { return kRowBlock * C::kRowBytes; }
@@ -197,6 +201,13 @@ struct TcParams {
     unsigned long long* final_out;   // [batch][nq][2]: written by the last CTA of each query block when merging in-kernel
     unsigned* counters;              // [batch][qblocks] arrival counters (zeroed by the launcher), null = no in-kernel merge
     int splits;
+    // [batch][nq] shared row thresholds (zeroed by the launcher), null = off.  Every CTA starts with an empty
+    // top-2, so for its first ~40 tiles the scan's exact-insertion path runs for most chunks; with the train
+    // set split over many CTAs per query row that warm-up dominated short CTAs (C3, C5, 8-GPU shards).  The
+    // CTAs of a row therefore publish the second-best dot they have found (atomicMax on a monotone code)
+    // and read the row's value back every few tiles: any published value is a lower bound of the row's final
+    // second best, so columns strictly below it are skipped without touching the result.
+    unsigned* row_floor;
     ExchangeArgs xch;                // xch.world > 1: the last CTA also exchanges with the peer GPUs (sharded database)
     long long q_blocks_valid;        // 256-row blocks present in qprep (CTAs beyond it are cluster padding)
     long long* trace;                // development aid (HM_I8_TRACE): per-tile clock64 stamps of CTA 0, else null
@@ -228,6 +239,12 @@ template <class Acc>
 struct Top2 {
     Acc v1, v2;                      // best / second-best dot (larger = closer)
     unsigned i1, i2;                 // train row local to this CTA's range
+    // Filter threshold f = max(v2, shared) where `shared` = (second-best dot some CTA of this row has already
+    // published, see TcParams::row_floor) - 2.  A column can only matter if its dot is > v2 (to enter the local
+    // top-2) and >= the published second best (to enter the row's final top-2; dots are even, so "> shared"):
+    // one compare against f skips everything else.  v2 only grows, so after an insertion
+    // max(v2_new, shared) = max(v2_new, f_old) and `shared` itself need not be kept.
+    Acc f;
 };
 
 __device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity, int* error_flag)
@@ -258,7 +275,7 @@ __device__ __forceinline__ void tmem_ld_fence64(uint32_t (&a)[64])
 // running second best decides whether anything can change the top-2.  Only then are the groups
 // revisited, and the exact (value, index) insertion runs for the groups that still qualify.
 // Strict '>' keeps the lowest train index on ties because columns are visited in ascending order.
-template <class C>
+template <class C, bool kFloor>
 __device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, unsigned limit,
                                            Top2<typename C::Acc>& s)
 {
@@ -272,21 +289,22 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, 
                         C::max2(C::from_bits(r[o + 6]), C::from_bits(r[o + 7])));
     }
     const Acc m = C::max3(gm[0], gm[1], C::max2(gm[2], gm[3]));
-    if (m > s.v2) {
+    if (m > (kFloor ? s.f : s.v2)) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-            if (gm[g] > s.v2) {
+            if (gm[g] > (kFloor ? s.f : s.v2)) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const Acc x = C::from_bits(r[g * 8 + e]);
                     const unsigned idx = colbase + g * 8 + e;
-                    if (x > s.v2 && idx < limit) {
+                    if (x > (kFloor ? s.f : s.v2) && idx < limit) {
                         if (x > s.v1) {
                             s.v2 = s.v1; s.i2 = s.i1;
                             s.v1 = x;    s.i1 = idx;
                         } else {
                             s.v2 = x;    s.i2 = idx;
                         }
+                        if (kFloor) s.f = C::max2(s.v2, s.f);
                     }
                 }
             }
@@ -311,7 +329,7 @@ __device__ __forceinline__ void issue_half(int h, uint32_t a_block, uint32_t b_s
     }
 }
 
-template <class C>
+template <class C, bool kFloor>
 __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
 {
     using Acc = typename C::Acc;
@@ -498,6 +516,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         Top2<Acc> s;
         s.v1 = s.v2 = C::lowest();
         s.i1 = s.i2 = 0;
+        s.f = C::floor_from(0);                           // below every possible dot
+        unsigned floor_code = 0;                          // largest threshold code read or published so far
         const long long first_row = (long long)tile_begin * kBlockN;
         const unsigned limit = (unsigned)min((long long)my_tiles * kBlockN, P.nt - first_row);
         int unit = mblk;                                  // (2 * i + mblk) % kUnits
@@ -507,6 +527,18 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             if (warp == 2 && lane == 0) trace_mark(P, i, 3);   // epilogue: accumulator complete
             if (warp == 9 && lane == 0) trace_mark(P, i, 5);
             ptx::tc_fence_after();
+            if constexpr (kFloor) {
+                if (i < 8 || (i & 3) == 0) {                 // every tile at first, then every fourth
+                    // the code loaded at the previous refresh is consumed now, so the load's latency is hidden
+                    s.f = C::max2(s.f, C::floor_from(floor_code));
+                    if (row < P.nq) {
+                        unsigned* floor_ptr = P.row_floor + ((long long)b * P.nq + row);
+                        const unsigned e = C::valid(s.v2) ? C::encode(s.v2) : 0u;
+                        if (e > floor_code) { atomicMax(floor_ptr, e); floor_code = e; }
+                        floor_code = max(floor_code, __ldcg(floor_ptr));
+                    }
+                }
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + unit * kBlockN + half * kCols;
             const unsigned colbase = (unsigned)i * kBlockN + half * kCols;
             if constexpr (C::kColSplit == 1) {
@@ -521,10 +553,10 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-                scan_chunk<C>(r0, colbase, limit, s);
-                scan_chunk<C>(r1, colbase + 32, limit, s);
-                scan_chunk<C>(r2, colbase + 64, limit, s);
-                scan_chunk<C>(r3, colbase + 96, limit, s);
+                scan_chunk<C, kFloor>(r0, colbase, limit, s);
+                scan_chunk<C, kFloor>(r1, colbase + 32, limit, s);
+                scan_chunk<C, kFloor>(r2, colbase + 64, limit, s);
+                scan_chunk<C, kFloor>(r3, colbase + 96, limit, s);
             } else {
                 uint32_t r[64];
 #if HM_TC_EXPERIMENT == 2
@@ -541,8 +573,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 if (r[lane] == 0x12345678u && r[32 + lane] == 0x9abcdef0u) s.i1 = colbase;   // keep the loads alive
 #else
                 // (one flat 64-column tree with a single branch was tried: 867 instead of 795 cycles per tile)
-                scan_chunk<C>(r, colbase, limit, s);
-                scan_chunk<C>(r + 32, colbase + 32, limit, s);
+                scan_chunk<C, kFloor>(r, colbase, limit, s);
+                scan_chunk<C, kFloor>(r + 32, colbase + 32, limit, s);
 #endif
 #endif
             }
@@ -589,19 +621,35 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     }
 }
 
-__global__ void __launch_bounds__(threads<CoreI8>(), 1) hm_i8_knn2_kernel(const TcParams P) { tc_knn2_body<CoreI8>(P); }
-__global__ void __launch_bounds__(threads<CoreF4>(), 1) hm_f4_knn2_kernel(const TcParams P) { tc_knn2_body<CoreF4>(P); }
+__global__ void __launch_bounds__(threads<CoreI8>(), 1) hm_i8_knn2_kernel(const TcParams P) { tc_knn2_body<CoreI8, false>(P); }
+__global__ void __launch_bounds__(threads<CoreF4>(), 1) hm_f4_knn2_kernel(const TcParams P) { tc_knn2_body<CoreF4, false>(P); }
+// the same kernels with the shared row thresholds (TcParams::row_floor): launched when the train set is split
+// over many short CTAs per query row
+__global__ void __launch_bounds__(threads<CoreI8>(), 1) hm_i8_knn2_floor_kernel(const TcParams P) { tc_knn2_body<CoreI8, true>(P); }
+__global__ void __launch_bounds__(threads<CoreF4>(), 1) hm_f4_knn2_floor_kernel(const TcParams P) { tc_knn2_body<CoreF4, true>(P); }
 
 using KernelFn = void (*)(const TcParams);
-template <class C> KernelFn kernel_of();
-template <> KernelFn kernel_of<CoreI8>() { return hm_i8_knn2_kernel; }
-template <> KernelFn kernel_of<CoreF4>() { return hm_f4_knn2_kernel; }
+template <class C> KernelFn kernel_of(bool floor = false);
+template <> KernelFn kernel_of<CoreI8>(bool floor) { return floor ? hm_i8_knn2_floor_kernel : hm_i8_knn2_kernel; }
+template <> KernelFn kernel_of<CoreF4>(bool floor) { return floor ? hm_f4_knn2_floor_kernel : hm_f4_knn2_kernel; }
 
 struct TcPlan {
     int ntiles, splits, tiles_per_split;
     int cluster;                     // CTAs per cluster (query blocks sharing the B tiles)
     long long qblocks;               // grid.x, rounded up to a multiple of `cluster`
 };
+
+// split launches whose CTAs have at most this many tiles use the shared-row-threshold kernels (HM_FLOOR_MAX_TILES
+// overrides for experiments)
+int floor_max_tiles()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HM_FLOOR_MAX_TILES");
+        v = e ? atoi(e) : 1300;   // f4, 2000 queries: 217 tiles per CTA +30 %, 433 +17 %, 865 +7 %, 1730 -3 %
+    }
+    return v;
+}
 
 int cluster_override()
 {
@@ -680,7 +728,7 @@ TcPlan plan_tc(long long nq, long long nt, int batch, int sm_count)
 
 long long padded_rows(long long n) { return ceil_div(n, kPadRows) * kPadRows; }
 
-// workspace layout: [256 B][arrival counters][partials][prepared q][prepared t]
+// workspace layout: [256 B][arrival counters | shared row thresholds][partials][prepared q][prepared t]
 template <class C>
 size_t partials_bytes(long long nq, long long nt, int batch, int sm_count)
 {
@@ -688,10 +736,13 @@ size_t partials_bytes(long long nq, long long nt, int batch, int sm_count)
     return (size_t)pl.splits * batch * nq * 2 * sizeof(unsigned long long);   // also when splits == 1 (partials mode)
 }
 
+// arrival counters followed by one 32-bit threshold code per query row (one memset clears both)
+inline size_t zeroed_bytes(long long row_blocks, long long rows) { return counters_bytes(row_blocks) + counters_bytes((rows + 1) / 2 * 2); }
+
 template <class C>
 size_t workspace_bytes_of(long long nq, long long nt, int batch, int sm_count, bool with_prepare)
 {
-    size_t b = 256 + counters_bytes(plan_tc<C>(nq, nt, batch, sm_count).qblocks * batch) + partials_bytes<C>(nq, nt, batch, sm_count);
+    size_t b = 256 + zeroed_bytes(plan_tc<C>(nq, nt, batch, sm_count).qblocks * batch, nq * batch) + partials_bytes<C>(nq, nt, batch, sm_count);
     b = (b + 1023) & ~(size_t)1023;
     if (with_prepare) b += (size_t)(padded_rows(nq) + padded_rows(nt)) * C::kRowBytes * batch;
     return b;
@@ -705,7 +756,8 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
 {
     static bool attr_set = false;
     if (!attr_set) {
-        HM_CUDA_CHECK(cudaFuncSetAttribute(kernel_of<C>(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()));
+        HM_CUDA_CHECK(cudaFuncSetAttribute(kernel_of<C>(false), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()));
+        HM_CUDA_CHECK(cudaFuncSetAttribute(kernel_of<C>(true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()));
         attr_set = true;
     }
     const TcPlan pl = plan_tc<C>(nq, nt, batch, sm_count);
@@ -714,7 +766,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
         return HM_ERR_UNSUPPORTED;
     }
     const bool keep_partials = out == nullptr;
-    const size_t cbytes = counters_bytes(pl.qblocks * batch);
+    const size_t cbytes = zeroed_bytes(pl.qblocks * batch, nq * batch);
     const size_t need = 256 + cbytes + partials_bytes<C>(nq, nt, batch, sm_count);
     if (!ws || ws_bytes < need) {
         set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
@@ -759,6 +811,8 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
     if ((pl.splits > 1 || fused_exchange) && !keep_partials) {   // merge in-kernel: last CTA per query block writes `out`
         P.counters = counters;
         P.final_out = out;
+        if (pl.splits > 1 && pl.tiles_per_split <= floor_max_tiles())
+            P.row_floor = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(counters) + counters_bytes(pl.qblocks * batch));
         HM_CUDA_CHECK(cudaMemsetAsync(counters, 0, cbytes, stream));
     } else if (!(pl.splits > 1 || keep_partials)) {
         P.out = out;
@@ -781,7 +835,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     profile_mark(true, stream);
-    cudaError_t le = cudaLaunchKernelEx(&cfg, kernel_of<C>(), P);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kernel_of<C>(P.row_floor != nullptr), P);
     profile_mark(false, stream);
     if (le != cudaSuccess) {
         set_error("cudaLaunchKernelEx(tensor-core k-NN kernel, cluster %d) failed: %s", pl.cluster, cudaGetErrorString(le));
