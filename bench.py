@@ -339,6 +339,7 @@ def run_b200(args):
         row_bytes = 256 if variant_used == "i8" else 128
         kind = "kind::i8" if variant_used == "i8" else "kind::mxf4"
         peak = mult * peaks["bf16_tflops_sustained"]
+        # shards whose CTAs see <= 1300 tiles run the *_floor twin of the kernel (shared row thresholds)
         roofline = {"bound": "tensor", "kernel": f"hm_{variant_used}_knn2_kernel", "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "note": f"+/-1 multiply-add ops (512/pair); peak = {mult:g} x bf16_tflops_sustained of {peak_src} "

@@ -259,3 +259,34 @@ def test_full_size_properties():
     assert np.array_equal(pdist, dist)         # distances are permutation invariant
     tie_free = dist[:, 0] != dist[:, 1]
     assert np.array_equal(perm[pidx[tie_free, 0]], idx[tie_free, 0])
+
+
+@pytest.mark.parametrize("variant", ("i8", "f4"))
+def test_split_launch_shared_row_thresholds(variant):
+    """Few query blocks against a long train set: the train dimension is split over many CTAs per query
+    row, which publish / read the row's second-best distance (floor kernels).  Ties across splits must still
+    resolve to the lowest trainIdx, bit-exact."""
+    rng = np.random.default_rng(77)
+    nq, nt = 300, 40000
+    # tie-heavy: one varying byte -> a handful of distinct distances, every row ties with thousands of others
+    t = np.zeros((nt, 32), np.uint8)
+    t[:, 5] = rng.integers(0, 4, nt)
+    q = np.zeros((nq, 32), np.uint8)
+    q[:, 5] = rng.integers(0, 4, nq)
+    assert np.array_equal(gpu_keys(q, t, variant), co.knn2_keys(q, t))
+    # all train rows equal: every pair ties, the answer is rows 0 and 1 for everybody
+    t[:] = 0x5A
+    assert np.array_equal(gpu_keys(q, t, variant), co.knn2_keys(q, t))
+    # uniform rows with exact copies of every query planted late, early and in the middle of the train set
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+    where = rng.choice(nt, (3, nq), replace=False)
+    for w in where:
+        t[w] = q
+    keys = gpu_keys(q, t, variant)
+    assert np.array_equal(keys, co.knn2_keys(q, t))
+    idx, dist, _ = nat.split_keys(keys)
+    assert (dist == 0).all() and np.array_equal(idx, np.sort(where, axis=0)[:2].T)
+    # distances all above 128 (negative dot products): complement-like rows only
+    t2 = (~q[rng.integers(0, nq, nt)]) ^ rng.integers(0, 2, (nt, 32), dtype=np.uint8)
+    assert np.array_equal(gpu_keys(q, t2, variant), co.knn2_keys(q, t2))
