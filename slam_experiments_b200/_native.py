@@ -418,6 +418,32 @@ def split_keys(keys: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
     return (k & np.uint64(0xFFFFFFFF)).astype(np.int64), (k >> np.uint64(32)).astype(np.int32), valid
 
 
+def locate_rows(starts: np.ndarray, gidx: np.ndarray):
+    """Global train rows -> ``(imgIdx, trainIdx)`` of cv2's collection API, given the first global row of
+    every train image (``starts``, length n_images + 1).  Equal-sized images (the usual fixed ORB budget)
+    are located by one division instead of a binary search (0.25 ms per 4000 rows against 4096 images)."""
+    n = len(starts) - 1
+    size = int(starts[1] - starts[0]) if n > 0 else 0
+    if size > 0 and int(starts[-1]) == size * n and _uniform_starts(starts, size):
+        img = gidx // size
+        return img.astype(np.int32), (gidx - img * size).astype(np.int32)
+    img = np.searchsorted(starts, gidx, side="right") - 1
+    return img.astype(np.int32), (gidx - starts[img]).astype(np.int32)
+
+
+_uniform_cache = {}
+
+
+def _uniform_starts(starts: np.ndarray, size: int) -> bool:
+    key = (starts.ctypes.data, len(starts), size)
+    hit = _uniform_cache.get(key)
+    if hit is None or hit[0] is not starts:
+        ok = bool((np.diff(starts) == size).all())
+        _uniform_cache.clear()
+        _uniform_cache[key] = hit = (starts, ok)
+    return hit[1]
+
+
 class HostContext:
     """``hm_context``: numpy in / numpy out through the C ABI alone (no torch tensors)."""
 

@@ -322,8 +322,9 @@ __device__ __forceinline__ void issue_half(int h, uint32_t a_block, uint32_t b_s
     for (int jj = 0; jj < kHalf; ++jj) {
         const int j = h * kHalf + jj;
         const int slab = j >> 2, k = j & 3;
-        const uint64_t da = ptx::make_kmajor_sw128_desc(a_block + slab * kSlabBytes + k * 32);
-        const uint64_t db = ptx::make_kmajor_sw128_desc(b_stage + slab * kSlabBytes + k * 32);
+        // a_block / b_stage are descriptor start-address fields (shared-memory address >> 4)
+        const uint64_t da = ptx::kmajor_sw128_desc_from_lo(a_block + ((slab * kSlabBytes + k * 32) >> 4));
+        const uint64_t db = ptx::kmajor_sw128_desc_from_lo(b_stage + ((slab * kSlabBytes + k * 32) >> 4));
         if constexpr (C::kScales) ptx::mma_mxf4_ss(tmem_d, da, db, idesc, tmem_sf, tmem_sf + 64, j != 0);
         else                      ptx::mma_i8_ss(tmem_d, da, db, idesc, j != 0);
     }
@@ -454,8 +455,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         // and blocking waits instead of the probes cost 70 cycles per tile.)
         const bool leader = ptx::elect_one();
         const uint32_t idesc = C::kScales ? ptx::make_mxf4_idesc(kRowBlock, kBlockN) : ptx::make_i8_idesc(kRowBlock, kBlockN);
-        const uint32_t a_addr = ptx::smem_u32(smem_a);
-        const uint32_t b_addr = ptx::smem_u32(smem_b);
+        const uint32_t a_addr = ptx::smem_u32(smem_a) >> 4;       // descriptor start-address fields
+        const uint32_t b_addr = ptx::smem_u32(smem_b) >> 4;
         const uint32_t tmem_sf = tmem_base + kScaleCol;
         if (has_a) bounded_wait(a_full_bar, 0, P.error_flag);
         int unit = 0;                                 // unit of the next work item
@@ -464,7 +465,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         for (int i = 0; i < my_tiles; ++i) {
             const int stage = i % kStages;
             const uint32_t use = i / kStages;
-            const uint32_t b_stage = b_addr + stage * kBStageBytes;
+            const uint32_t b_stage = b_addr + stage * (kBStageBytes >> 4);
             const int unit_a = unit;
             const uint32_t par_a = upar;
             if (++unit == kUnits) { unit = 0; upar ^= 1; }
@@ -489,7 +490,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             if (!ready1) bounded_wait(&tmem_empty_bar[unit_b], par_b, P.error_flag);
             if (leader) trace_mark(P, i, 6);           // second unit free
             ptx::tc_fence_after();
-            if (leader) issue_half<C>(0, a_addr + kRowBlockBytes, b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
+            if (leader) issue_half<C>(0, a_addr + (kRowBlockBytes >> 4), b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
             ready0 = false;
             if (i + 1 < my_tiles) {
                 const int n = i + 1;
@@ -497,7 +498,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                                                      ptx::mbar_test_wait(&tmem_empty_bar[unit], upar));
             }
             if (leader) {
-                issue_half<C>(1, a_addr + kRowBlockBytes, b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
+                issue_half<C>(1, a_addr + (kRowBlockBytes >> 4), b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
                 ptx::tc_commit(&tmem_full_bar[unit_b]);
                 // smem stage reusable (by every producer of the cluster) once these MMAs retire
                 if (cs > 1) ptx::tc_commit_multicast(&empty_bar[stage], cmask);

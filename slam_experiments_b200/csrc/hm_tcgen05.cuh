@@ -247,6 +247,14 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr)
     return d;
 }
 
+// The same descriptor from its start-address field (smem_addr >> 4, fits 14 bits for any shared-memory
+// address): advancing the operand by `bytes` is `lo + (bytes >> 4)` -- one add, no shift / mask per MMA.
+constexpr uint32_t kKmajorSw128DescHi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t kmajor_sw128_desc_from_lo(uint32_t lo)
+{
+    return ((uint64_t)kKmajorSw128DescHi << 32) | lo;
+}
+
 // Instruction descriptor for kind::i8, dense, no saturate:
 //   [4,6) D format = 2 (S32)   [7,10) A format = 1 (signed 8-bit)   [10,13) B format = 1
 //   bit 15 / 16: A / B major = 0 (K-major)   [17,23) N >> 3   [24,29) M >> 4

@@ -350,8 +350,7 @@ class BFMatcher:
         if kk == 0:
             return tuple(() for _ in range(nq))
         gidx, dist = gidx[:, :kk], dist[:, :kk]
-        img = np.searchsorted(self._train_starts, gidx, side="right") - 1
-        local = gidx - self._train_starts[img]
+        img, local = nat.locate_rows(self._train_starts, gidx)
         qi = np.repeat(np.arange(nq, dtype=np.int32), kk)
         return _build_dmatches(qi, local.reshape(-1), dist.reshape(-1), img.reshape(-1), rows=kk)
 

@@ -273,8 +273,7 @@ class ShardedKeyframeDatabase:
         gidx, dist, valid = nat.split_keys(keys)
         kk = min(k, int(valid[0].sum()))
         gidx, dist = gidx[:, :kk], dist[:, :kk]
-        img = (np.searchsorted(self.starts, gidx, side="right") - 1).astype(np.int32)
-        local = (gidx - self.starts[img]).astype(np.int32)
+        img, local = nat.locate_rows(self.starts, gidx)
         return img, local, dist
 
     def knnMatch(self, queryDescriptors, k: int = 2) -> tuple:
