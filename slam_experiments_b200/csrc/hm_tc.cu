@@ -39,6 +39,11 @@
 #include "hm_common.cuh"
 #include "hm_tcgen05.cuh"
 
+// train rows per tile of the kind::mxf4 core: 128 (three accumulator units) or 96 (four)
+#ifndef HM_F4_TILE_N
+#define HM_F4_TILE_N 128
+#endif
+
 namespace hm {
 
 namespace {
@@ -46,7 +51,7 @@ namespace {
 constexpr int kRowBlock = 128;               // rows per prepared block = UMMA M = tile N
 constexpr int kMBlocks = 2;                  // A blocks per CTA
 constexpr int kBlockM = kRowBlock * kMBlocks;   // 256 queries per CTA
-constexpr int kBlockN = kRowBlock;           // train rows per tile
+// train rows per tile = MMA N: a per-core constant (C::kTileN)
 constexpr int kSlabBytes = kRowBlock * 128;  // 16 KB: 128 rows x 128 bytes of K
 constexpr int kPadRows = HM_PREPARED_TILE_ROWS;
 constexpr int kTmemCols = 512;
@@ -54,15 +59,16 @@ constexpr int kTmemCols = 512;
 // and per 128 / kColSplit columns of a tile
 constexpr uint32_t kSpinLimit = 1u << 26;
 
-static_assert(kPadRows % kBlockN == 0 && kPadRows % kBlockM == 0, "prepared padding must cover whole tiles");
+static_assert(kPadRows % kBlockM == 0, "prepared padding must cover whole query blocks");
 
 // ---- the two cores ---------------------------------------------------------------------------
 struct CoreI8 {
     using Acc = int;
     static constexpr int kSlabs = 2;                         // 128-byte K slabs per row
     static constexpr int kRowBytes = HM_PREPARED_ROW_BYTES;  // 256
+    static constexpr int kTileN = 128;                       // train rows per tile (one prepared row block)
     static constexpr int kStages = 4;                        // 4 x 32 KB in flight
-    static constexpr int kUnits = 4;                         // accumulator units of 128 TMEM columns
+    static constexpr int kUnits = 4;                         // accumulator units of kTileN TMEM columns
     static constexpr int kColSplit = 1;                      // 8 epilogue warps: the MMA (and the power cap) paces this core
     static constexpr bool kScales = false;
     static constexpr int kPrologueTiles = 4;                 // fixed per-CTA cost in tile times (split planning)
@@ -80,14 +86,20 @@ struct CoreF4 {
     using Acc = float;
     static constexpr int kSlabs = 1;
     static constexpr int kRowBytes = HM_PREPARED_F4_ROW_BYTES;  // 128
-    static constexpr int kStages = 8;                        // 8 x 16 KB in flight (a tile lasts half as long)
-    static constexpr int kUnits = 3;                         // columns [0, 384); scale factors in [384, 512)
+    // The e2m1 image is a flat sequence of 8-row swizzle atoms, so any tile height that is a multiple of 8 is
+    // one contiguous bulk copy.  96-row tiles let FOUR accumulator units fit beside the scale factors
+    // (4 x 96 = 384 columns) and were tried to give the issuer more slack when an epilogue warp takes the
+    // exact-insertion path: bit-exact, but 903 instead of 785 cycles per 128 columns on C4 (per-tile costs of
+    // the issuer and of the epilogue warps do not shrink with the tile) -- so 128 rows and three units.
+    static constexpr int kTileN = HM_F4_TILE_N;
+    static constexpr int kStages = HM_F4_TILE_N == 96 ? 10 : 8;   // x 12 / 16 KB in flight (a tile lasts half as long)
+    static constexpr int kUnits = HM_F4_TILE_N == 96 ? 4 : 3;     // columns [0, 384); scale factors in [384, 512)
     // 16 epilogue warps, two per (query block, lane quarter), 64 columns each: with 8 the scan is latency
     // bound (ncu r01j: issue slots 37 %, ALU 46 %, top stalls wait / long scoreboard) at 1087 cycles per
     // tile while the MMAs need 512
     static constexpr int kColSplit = 2;
     static constexpr bool kScales = true;
-    static constexpr int kPrologueTiles = 8;
+    static constexpr int kPrologueTiles = 10;
     static __device__ __forceinline__ Acc lowest() { return -INFINITY; }
     static __device__ __forceinline__ Acc from_bits(uint32_t x) { return __uint_as_float(x); }
     static __device__ __forceinline__ Acc max3(Acc a, Acc b, Acc c) { return fmaxf(fmaxf(a, b), c); }   // FMNMX3
@@ -100,7 +112,7 @@ struct CoreF4 {
 
 template <class C> __host__ __device__ constexpr int row_block_bytes() { return kRowBlock * C::kRowBytes; }
 template <class C> __host__ __device__ constexpr int a_bytes() { return kMBlocks * row_block_bytes<C>(); }
-template <class C> __host__ __device__ constexpr int b_stage_bytes() { return row_block_bytes<C>(); }
+template <class C> __host__ __device__ constexpr int b_stage_bytes() { return C::kTileN * C::kRowBytes; }
 template <class C> __host__ __device__ constexpr int epilogue_warps() { return 4 * kMBlocks * C::kColSplit; }
 template <class C> __host__ __device__ constexpr int threads() { return 32 * (2 + epilogue_warps<C>()); }
 // + 256 B of barriers, + 4 KB where the epilogue warps of the upper column halves hand over their keys
@@ -108,7 +120,8 @@ constexpr int kHandoverBytes = kBlockM * 16;
 template <class C> __host__ __device__ constexpr int smem_bytes() { return 1024 + a_bytes<C>() + C::kStages * b_stage_bytes<C>() + 256 + kHandoverBytes; }
 static_assert((2 * CoreF4::kStages + 1 + 2 * CoreF4::kUnits) * 8 + 16 <= 256, "barrier block");
 static_assert((2 * CoreI8::kStages + 1 + 2 * CoreI8::kUnits) * 8 + 16 <= 256, "barrier block");
-constexpr int kScaleCol = CoreF4::kUnits * kBlockN;          // first scale-factor column (384)
+constexpr int kScaleCol = CoreF4::kUnits * CoreF4::kTileN;   // first scale-factor column (384)
+static_assert(kScaleCol + 128 <= kTmemCols, "scale factors must fit");
 
 // ------------------------------------------------------------------------------------------
 // hm_prepare: packed bits -> +/-1 in the tiled swizzled layout.  One thread writes one 16-byte
@@ -265,6 +278,10 @@ __device__ __forceinline__ void tmem_ld_fence4(uint32_t (&a)[32], uint32_t (&b)[
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(a), HM_R32(b), HM_R32(c), HM_R32(d) : : "memory");
 }
+__device__ __forceinline__ void tmem_ld_fence48(uint32_t (&a)[32], uint32_t (&b)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(a), HM_R8(b, 0), HM_R8(b, 8) : : "memory");
+}
 __device__ __forceinline__ void tmem_ld_fence64(uint32_t (&a)[64])
 {
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R8(a, 0), HM_R8(a, 8), HM_R8(a, 16), HM_R8(a, 24), HM_R8(a, 32), HM_R8(a, 40), HM_R8(a, 48), HM_R8(a, 56) : : "memory");
@@ -275,23 +292,23 @@ __device__ __forceinline__ void tmem_ld_fence64(uint32_t (&a)[64])
 // running second best decides whether anything can change the top-2.  Only then are the groups
 // revisited, and the exact (value, index) insertion runs for the groups that still qualify.
 // Strict '>' keeps the lowest train index on ties because columns are visited in ascending order.
-template <class C, bool kFloor>
+template <class C, bool kFloor, int kGroups = 4>
 __device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, unsigned limit,
                                            Top2<typename C::Acc>& s)
 {
     using Acc = typename C::Acc;
     Acc gm[4];
 #pragma unroll
-    for (int g = 0; g < 4; ++g) {
+    for (int g = 0; g < kGroups; ++g) {
         const int o = g * 8;
         gm[g] = C::max3(C::max3(C::from_bits(r[o]), C::from_bits(r[o + 1]), C::from_bits(r[o + 2])),
                         C::max3(C::from_bits(r[o + 3]), C::from_bits(r[o + 4]), C::from_bits(r[o + 5])),
                         C::max2(C::from_bits(r[o + 6]), C::from_bits(r[o + 7])));
     }
-    const Acc m = C::max3(gm[0], gm[1], C::max2(gm[2], gm[3]));
+    const Acc m = kGroups == 4 ? C::max3(gm[0], gm[1], C::max2(gm[2], gm[3])) : C::max2(gm[0], gm[1]);
     if (m > (kFloor ? s.f : s.v2)) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < kGroups; ++g) {
             if (gm[g] > (kFloor ? s.f : s.v2)) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
@@ -339,6 +356,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     constexpr int kABytes = a_bytes<C>();
     constexpr int kBStageBytes = b_stage_bytes<C>();
     constexpr int kRowBlockBytes = row_block_bytes<C>();
+    constexpr int kTileN = C::kTileN;
 
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment
@@ -430,7 +448,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 trace_mark(P, i, 0);                      // producer: stage free, copy issued
                 ptx::mbar_arrive_expect_tx(&full_bar[stage], kBStageBytes);
                 uint8_t* dst = smem_b + stage * kBStageBytes + crank * piece;
-                const uint8_t* src = tsrc + (long long)(tile_begin + i) * kRowBlockBytes + crank * piece;
+                const uint8_t* src = tsrc + (long long)(tile_begin + i) * kBStageBytes + crank * piece;
                 if (cs > 1) ptx::bulk_g2s_multicast(dst, src, piece, &full_bar[stage], cmask);
                 else        ptx::bulk_g2s(dst, src, piece, &full_bar[stage]);
             }
@@ -454,7 +472,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         // mbarrier.arrive.release.cluster costs the arriving thread ~2000 cycles per call (relaxed: none),
         // and blocking waits instead of the probes cost 70 cycles per tile.)
         const bool leader = ptx::elect_one();
-        const uint32_t idesc = C::kScales ? ptx::make_mxf4_idesc(kRowBlock, kBlockN) : ptx::make_i8_idesc(kRowBlock, kBlockN);
+        const uint32_t idesc = C::kScales ? ptx::make_mxf4_idesc(kRowBlock, kTileN) : ptx::make_i8_idesc(kRowBlock, kTileN);
         const uint32_t a_addr = ptx::smem_u32(smem_a) >> 4;       // descriptor start-address fields
         const uint32_t b_addr = ptx::smem_u32(smem_b) >> 4;
         const uint32_t tmem_sf = tmem_base + kScaleCol;
@@ -480,17 +498,17 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             if (leader) trace_mark(P, i, 1);           // operands landed, first unit free
             ptx::tc_fence_after();
             // ---- query block 0 ----
-            if (leader) issue_half<C>(0, a_addr, b_stage, tmem_base + unit_a * kBlockN, idesc, tmem_sf);
+            if (leader) issue_half<C>(0, a_addr, b_stage, tmem_base + unit_a * kTileN, idesc, tmem_sf);
             const bool ready1 = __all_sync(0xffffffffu, ptx::mbar_test_wait(&tmem_empty_bar[unit_b], par_b));
             if (leader) {
-                issue_half<C>(1, a_addr, b_stage, tmem_base + unit_a * kBlockN, idesc, tmem_sf);
+                issue_half<C>(1, a_addr, b_stage, tmem_base + unit_a * kTileN, idesc, tmem_sf);
                 ptx::tc_commit(&tmem_full_bar[unit_a]);    // query block 0's accumulator is ready
             }
             // ---- query block 1 ----
             if (!ready1) bounded_wait(&tmem_empty_bar[unit_b], par_b, P.error_flag);
             if (leader) trace_mark(P, i, 6);           // second unit free
             ptx::tc_fence_after();
-            if (leader) issue_half<C>(0, a_addr + (kRowBlockBytes >> 4), b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
+            if (leader) issue_half<C>(0, a_addr + (kRowBlockBytes >> 4), b_stage, tmem_base + unit_b * kTileN, idesc, tmem_sf);
             ready0 = false;
             if (i + 1 < my_tiles) {
                 const int n = i + 1;
@@ -498,7 +516,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                                                      ptx::mbar_test_wait(&tmem_empty_bar[unit], upar));
             }
             if (leader) {
-                issue_half<C>(1, a_addr + (kRowBlockBytes >> 4), b_stage, tmem_base + unit_b * kBlockN, idesc, tmem_sf);
+                issue_half<C>(1, a_addr + (kRowBlockBytes >> 4), b_stage, tmem_base + unit_b * kTileN, idesc, tmem_sf);
                 ptx::tc_commit(&tmem_full_bar[unit_b]);
                 // smem stage reusable (by every producer of the cluster) once these MMAs retire
                 if (cs > 1) ptx::tc_commit_multicast(&empty_bar[stage], cmask);
@@ -508,7 +526,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         __syncwarp();
     } else {
         // ===== epilogue: TMEM -> registers, running top-2 per query row =====
-        constexpr int kCols = kBlockN / C::kColSplit;     // train columns of a tile this warp scans
+        constexpr int kCols = kTileN / C::kColSplit;      // train columns of a tile this warp scans
         const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
         const int mblk = ((warp - 2) >> 2) & 1;           // which 128-row query block of the CTA
         const int half = (warp - 2) >> 3;                 // which column range of every tile (0 when kColSplit == 1)
@@ -519,8 +537,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         s.i1 = s.i2 = 0;
         s.f = C::floor_from(0);                           // below every possible dot
         unsigned floor_code = 0;                          // largest threshold code read or published so far
-        const long long first_row = (long long)tile_begin * kBlockN;
-        const unsigned limit = (unsigned)min((long long)my_tiles * kBlockN, P.nt - first_row);
+        const long long first_row = (long long)tile_begin * kTileN;
+        const unsigned limit = (unsigned)min((long long)my_tiles * kTileN, P.nt - first_row);
         int unit = mblk;                                  // (2 * i + mblk) % kUnits
         uint32_t unit_use = 0;                            // (2 * i + mblk) / kUnits
         for (int i = 0; i < my_tiles; ++i) {
@@ -540,8 +558,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     }
                 }
             }
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + unit * kBlockN + half * kCols;
-            const unsigned colbase = (unsigned)i * kBlockN + half * kCols;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + unit * kTileN + half * kCols;
+            const unsigned colbase = (unsigned)i * kTileN + half * kCols;
             if constexpr (C::kColSplit == 1) {
                 // all four 32-column loads are issued before the first scan so their latencies overlap
                 uint32_t r0[32], r1[32], r2[32], r3[32];
@@ -559,25 +577,28 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 scan_chunk<C, kFloor>(r2, colbase + 64, limit, s);
                 scan_chunk<C, kFloor>(r3, colbase + 96, limit, s);
             } else {
-                uint32_t r[64];
-#if HM_TC_EXPERIMENT == 2
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-#else
-                ptx::tmem_ld_32x64(taddr, r);
-                tmem_ld_fence64(r);
-                ptx::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-#if HM_TC_EXPERIMENT == 1
-                if (r[lane] == 0x12345678u && r[32 + lane] == 0x9abcdef0u) s.i1 = colbase;   // keep the loads alive
-#else
-                // (one flat 64-column tree with a single branch was tried: 867 instead of 795 cycles per tile)
-                scan_chunk<C, kFloor>(r, colbase, limit, s);
-                scan_chunk<C, kFloor>(r + 32, colbase + 32, limit, s);
-#endif
-#endif
+                if constexpr (kCols == 64) {
+                    uint32_t r[64];
+                    ptx::tmem_ld_32x64(taddr, r);
+                    tmem_ld_fence64(r);
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
+                    // (one flat 64-column tree with a single branch was tried: 867 instead of 795 cycles per tile)
+                    scan_chunk<C, kFloor>(r, colbase, limit, s);
+                    scan_chunk<C, kFloor>(r + 32, colbase + 32, limit, s);
+                } else {
+                    static_assert(kCols == 64 || kCols == 48, "column split");
+                    uint32_t r0[32], r1[16];
+                    ptx::tmem_ld_32x32(taddr, r0);
+                    ptx::tmem_ld_32x16(taddr + 32, r1);
+                    tmem_ld_fence48(r0, r1);
+                    ptx::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
+                    scan_chunk<C, kFloor>(r0, colbase, limit, s);
+                    scan_chunk<C, kFloor, 2>(r1, colbase + 32, limit, s);
+                }
             }
             unit += 2;
             if (unit >= kUnits) { unit -= kUnits; ++unit_use; }
@@ -705,7 +726,7 @@ TcPlan plan_tc(long long nq, long long nt, int batch, int sm_count)
     if (cluster_override()) pl.cluster = cluster_override();
     pl.qblocks = ceil_div(qb, pl.cluster) * pl.cluster;
     sm_count = resident_ctas<C>(pl.cluster, sm_count);
-    pl.ntiles = (int)ceil_div(nt, kBlockN);
+    pl.ntiles = (int)ceil_div(nt, C::kTileN);
     const long long items = pl.qblocks * batch;
     // choose the split count minimising (waves) x (tiles per CTA + fixed prologue worth a few tiles)
     long long best_cost = -1;
@@ -727,7 +748,9 @@ TcPlan plan_tc(long long nq, long long nt, int batch, int sm_count)
     return pl;
 }
 
-long long padded_rows(long long n) { return ceil_div(n, kPadRows) * kPadRows; }
+// rows of a prepared image: whole tiles of the core's height, rounded up to whole 256-row query blocks
+template <class C>
+long long padded_rows(long long n) { return ceil_div(ceil_div(n, C::kTileN) * C::kTileN, kPadRows) * kPadRows; }
 
 // workspace layout: [256 B][arrival counters | shared row thresholds][partials][prepared q][prepared t]
 template <class C>
@@ -745,7 +768,7 @@ size_t workspace_bytes_of(long long nq, long long nt, int batch, int sm_count, b
 {
     size_t b = 256 + zeroed_bytes(plan_tc<C>(nq, nt, batch, sm_count).qblocks * batch, nq * batch) + partials_bytes<C>(nq, nt, batch, sm_count);
     b = (b + 1023) & ~(size_t)1023;
-    if (with_prepare) b += (size_t)(padded_rows(nq) + padded_rows(nt)) * C::kRowBytes * batch;
+    if (with_prepare) b += (size_t)(padded_rows<C>(nq) + padded_rows<C>(nt)) * C::kRowBytes * batch;
     return b;
 }
 
@@ -762,7 +785,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
         attr_set = true;
     }
     const TcPlan pl = plan_tc<C>(nq, nt, batch, sm_count);
-    if ((long long)pl.ntiles * kBlockN > (1ll << 32)) {
+    if ((long long)pl.ntiles * C::kTileN > (1ll << 32)) {
         set_error("train set too large for 32-bit trainIdx");
         return HM_ERR_UNSUPPORTED;
     }
@@ -777,8 +800,8 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
     P.qprep = static_cast<const uint8_t*>(qprep);
     P.tprep = static_cast<const uint8_t*>(tprep);
     P.nq = nq; P.nt = nt;
-    P.q_padded = padded_rows(nq);
-    P.t_padded = padded_rows(nt);
+    P.q_padded = padded_rows<C>(nq);
+    P.t_padded = padded_rows<C>(nt);
     P.tiles_per_split = pl.tiles_per_split;
     P.ntiles = pl.ntiles;
     P.train_base = train_base;
@@ -874,7 +897,7 @@ int launch_prepare_of(const uint8_t* bits, long long n, long long stride, long l
     if (n <= 0 || batch <= 0) return HM_OK;
     PrepareParams P{};
     P.bits = bits; P.n = n; P.stride = stride; P.batch_stride = batch_stride;
-    P.padded_rows = padded_rows(n);
+    P.padded_rows = padded_rows<C>(n);
     P.out = static_cast<uint8_t*>(prepared);
     const long long chunks = P.padded_rows * (C::kRowBytes / 16);
     dim3 grid((unsigned)ceil_div(chunks, 256), (unsigned)batch);
@@ -894,7 +917,7 @@ int launch_knn2_of(const KnnProblem& p, unsigned long long* out, void* ws, size_
     }
     const size_t head = workspace_bytes_of<C>(p.nq, p.nt, p.batch, sm_count, false);
     uint8_t* qprep = static_cast<uint8_t*>(ws) + head;
-    uint8_t* tprep = qprep + (size_t)padded_rows(p.nq) * C::kRowBytes * p.batch;
+    uint8_t* tprep = qprep + (size_t)padded_rows<C>(p.nq) * C::kRowBytes * p.batch;
     int rc = launch_prepare_of<C>(p.q, p.nq, p.q_stride, p.q_batch_stride, p.batch, qprep, stream);
     if (rc != HM_OK) return rc;
     rc = launch_prepare_of<C>(p.t, p.nt, p.t_stride, p.t_batch_stride, p.batch, tprep, stream);
@@ -908,7 +931,7 @@ int launch_knn2_of(const KnnProblem& p, unsigned long long* out, void* ws, size_
 // ---- core dispatch (variant must be HM_VARIANT_I8 or HM_VARIANT_F4) ---------------------------
 size_t prepared_bytes(long long n, int variant)
 {
-    return (size_t)padded_rows(n) * (variant == HM_VARIANT_F4 ? CoreF4::kRowBytes : CoreI8::kRowBytes);
+    return variant == HM_VARIANT_F4 ? (size_t)padded_rows<CoreF4>(n) * CoreF4::kRowBytes : (size_t)padded_rows<CoreI8>(n) * CoreI8::kRowBytes;
 }
 
 int launch_prepare(const uint8_t* bits, long long n, long long stride, long long batch_stride, int batch,
