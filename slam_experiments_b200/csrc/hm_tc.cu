@@ -584,7 +584,10 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-                    // (one flat 64-column tree with a single branch was tried: 867 instead of 795 cycles per tile)
+                    // (tried and slower, C4 cycles per tile against 785: one flat 64-column tree with a single branch 867;
+                    // warp-uniform votes around the insertion path 871; software pipelining over half items -- two
+                    // 32-register buffers, the next item's first half loaded while this item's second half is
+                    // scanned -- 882)
                     scan_chunk<C, kFloor>(r, colbase, limit, s);
                     scan_chunk<C, kFloor>(r + 32, colbase + 32, limit, s);
                 } else {
