@@ -190,6 +190,17 @@ HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, in
                           uint64_t* out_keys,
                           int variant, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- consumer of the match list: replaces the two list-building loops of
+ *      /root/reference/utils.py:13-19 (pose_estimation_2d2d) and :41-47 (triangulation) ------------- */
+/* For every problem b and every match m < count[b] of a match list (q_idx / t_idx / count as written by
+ * hm_filter_matches / hm_match_fused, `stride` = elements per problem = its nq):
+ *     out_query_pts[b][m] = query_pts[b][q_idx[b][m]]     (current frame, features[m.queryIdx].position)
+ *     out_train_pts[b][m] = train_pts[b][t_idx[b][m]]     (last frame,    features[m.trainIdx].position)
+ * Points are (x, y) int32 pairs, 8-byte aligned; entries at m >= count[b] are left untouched. */
+HM_API int hm_gather_points(const int32_t* q_idx, const int32_t* t_idx, const int32_t* count, int64_t stride, int batch,
+                            const int32_t* query_pts, int64_t nq, const int32_t* train_pts, int64_t nt,
+                            int32_t* out_query_pts, int32_t* out_train_pts, void* stream);
+
 /* ---- host-buffer convenience (what a non-torch caller binds) --------------------------- */
 typedef struct hm_context hm_context; /* owns a stream, device scratch and pinned staging */
 HM_API int hm_context_create(hm_context** out_ctx);

@@ -32,7 +32,7 @@ PREPARED_ROW_BYTES = {VARIANT_I8: 256, VARIANT_F4: 128}
 EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
     "hm_knn2", "hm_knn2_batched", "hm_default_tensor_variant", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials", "hm_knn2_prepared_exchange",
-    "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused",
+    "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused", "hm_gather_points",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host",
 )
 
@@ -85,6 +85,8 @@ def _declare(L):
     L.hm_match_fused.restype = ci
     L.hm_match_fused.argtypes = [vp, i64, i64, i64, vp, i64, i64, i64, ci, cu, vp, c.c_double,
                                  vp, vp, vp, vp, vp, ci, vp, sz, vp]
+    L.hm_gather_points.restype = ci
+    L.hm_gather_points.argtypes = [vp, vp, vp, i64, ci, vp, i64, vp, i64, vp, vp, vp]
     L.hm_context_create.restype = ci
     L.hm_context_create.argtypes = [c.POINTER(vp)]
     L.hm_context_destroy.restype = None
@@ -386,6 +388,27 @@ def match_fused(query: torch.Tensor, train: torch.Tensor, ratio: Optional[float]
                                _stream_ptr(dev)), "hm_match_fused")
     del lut
     return (oq, ot, od, cnt, keys) if want_keys else (oq, ot, od, cnt)
+
+
+def gather_points(q_idx: torch.Tensor, t_idx: torch.Tensor, count: torch.Tensor, query_pts: torch.Tensor,
+                  train_pts: torch.Tensor):
+    """``hm_gather_points``: packed matched-point arrays from a device match list.
+
+    ``q_idx`` / ``t_idx`` ``[B, nq]`` int32 and ``count`` ``[B]`` as returned by :func:`match_fused`;
+    ``query_pts`` ``[B, nq, 2]`` / ``train_pts`` ``[B, nt, 2]`` int32.  Returns ``(out_query, out_train)``
+    ``[B, nq, 2]`` int32; rows ``>= count[b]`` are undefined."""
+    for t, name in ((query_pts, "query_pts"), (train_pts, "train_pts")):
+        if t.dtype != torch.int32 or t.dim() != 3 or t.shape[2] != 2 or not t.is_cuda or not t.is_contiguous():
+            raise ValueError(f"{name} must be a contiguous CUDA int32 tensor [B, N, 2]")
+    b, stride = q_idx.shape
+    dev = q_idx.device
+    oq = torch.empty((b, stride, 2), dtype=torch.int32, device=dev)
+    ot = torch.empty((b, stride, 2), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().hm_gather_points(q_idx.data_ptr(), t_idx.data_ptr(), count.data_ptr(), stride, b,
+                                     query_pts.data_ptr(), query_pts.shape[1], train_pts.data_ptr(), train_pts.shape[1],
+                                     oq.data_ptr(), ot.data_ptr(), _stream_ptr(dev)), "hm_gather_points")
+    return oq, ot
 
 
 def profile_events(start: Optional[torch.cuda.Event], stop: Optional[torch.cuda.Event]) -> None:

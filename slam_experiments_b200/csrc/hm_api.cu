@@ -471,6 +471,24 @@ HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, in
     return launch_filter(fwd, nq, bwd, nt, batch, flags, lut, thr, out_q, out_t, out_d, out_count, st);
 }
 
+HM_API int hm_gather_points(const int32_t* q_idx, const int32_t* t_idx, const int32_t* count, int64_t stride, int batch,
+                            const int32_t* query_pts, int64_t nq, const int32_t* train_pts, int64_t nt,
+                            int32_t* out_query_pts, int32_t* out_train_pts, void* stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (batch <= 0 || stride <= 0) return HM_OK;
+    if (!q_idx || !t_idx || !count || !query_pts || !train_pts || !out_query_pts || !out_train_pts || nq <= 0 || nt <= 0 ||
+        ((reinterpret_cast<uintptr_t>(query_pts) | reinterpret_cast<uintptr_t>(train_pts) |
+          reinterpret_cast<uintptr_t>(out_query_pts) | reinterpret_cast<uintptr_t>(out_train_pts)) & 7)) {
+        set_error("hm_gather_points: null, empty or misaligned argument");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    return launch_gather_points(q_idx, t_idx, count, stride, batch, query_pts, nq, train_pts, nt, out_query_pts,
+                                out_train_pts, static_cast<cudaStream_t>(stream));
+}
+
 // ---- host-buffer convenience ---------------------------------------------------------------
 struct hm_context {
     cudaStream_t stream;

@@ -213,4 +213,50 @@ int launch_filter(const unsigned long long* fwd, long long nq, const unsigned lo
     return HM_OK;
 }
 
+// ---- consumer of the match list ------------------------------------------------
+// /root/reference/utils.py:13-19 and :41-47 build two point lists with a Python loop over the matches
+// (source_frame.features[m.trainIdx].position, query_frame.features[m.queryIdx].position); here the
+// keypoint positions stay resident next to the descriptors and the two packed (M, 2) arrays are gathered
+// on the device from the match list the filter kernel produced.
+struct GatherParams {
+    const int* q_idx;
+    const int* t_idx;
+    const int* count;
+    long long stride;                // match-list elements per problem
+    const int2* query_pts;           // [batch][nq]
+    const int2* train_pts;           // [batch][nt]
+    long long nq, nt;
+    int2* out_query;
+    int2* out_train;
+};
+
+__global__ void __launch_bounds__(256) hm_gather_points_kernel(const GatherParams P)
+{
+    const int b = blockIdx.y;
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= P.count[b]) return;
+    const long long o = (long long)b * P.stride + m;
+    const int q = P.q_idx[o], t = P.t_idx[o];
+    P.out_query[o] = P.query_pts[(long long)b * P.nq + q];
+    P.out_train[o] = P.train_pts[(long long)b * P.nt + t];
+}
+
+int launch_gather_points(const int* q_idx, const int* t_idx, const int* count, long long stride, int batch,
+                         const int* query_pts, long long nq, const int* train_pts, long long nt, int* out_query,
+                         int* out_train, cudaStream_t stream)
+{
+    if (batch <= 0 || stride <= 0) return HM_OK;
+    GatherParams P{};
+    P.q_idx = q_idx; P.t_idx = t_idx; P.count = count; P.stride = stride;
+    P.query_pts = reinterpret_cast<const int2*>(query_pts);
+    P.train_pts = reinterpret_cast<const int2*>(train_pts);
+    P.nq = nq; P.nt = nt;
+    P.out_query = reinterpret_cast<int2*>(out_query);
+    P.out_train = reinterpret_cast<int2*>(out_train);
+    dim3 grid((unsigned)ceil_div(stride, 256), (unsigned)batch);
+    hm_gather_points_kernel<<<grid, 256, 0, stream>>>(P);
+    HM_CUDA_CHECK(cudaGetLastError());
+    return HM_OK;
+}
+
 }  // namespace hm

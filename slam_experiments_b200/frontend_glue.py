@@ -92,6 +92,7 @@ class FrameDescriptorStore:
         self.capacity = int(capacity)
         self.ratio, self.cross_check, self.variant = ratio, bool(cross_check), variant
         self._frames: "OrderedDict[Any, torch.Tensor]" = OrderedDict()
+        self._points: dict = {}                                   # frame_id -> [N, 2] int32 pixel positions on the device
         self._pin: Optional[torch.Tensor] = None
 
     def __contains__(self, frame_id) -> bool:
@@ -100,7 +101,9 @@ class FrameDescriptorStore:
     def __len__(self) -> int:
         return len(self._frames)
 
-    def put(self, frame_id, descriptors) -> torch.Tensor:
+    def put(self, frame_id, descriptors, positions=None) -> torch.Tensor:
+        """Upload a frame once.  ``positions`` (optional ``[N, 2]`` pixel coordinates, truncated to int32 like
+        ``Feature.position``) stay resident too, so that :meth:`matched_points` can gather on the device."""
         a = np.asarray(descriptors) if not isinstance(descriptors, torch.Tensor) else descriptors
         if isinstance(a, np.ndarray):
             if a.size == 0:
@@ -123,8 +126,18 @@ class FrameDescriptorStore:
             t = a.to(self.device).contiguous()
         self._frames[frame_id] = t
         self._frames.move_to_end(frame_id)
+        self._points.pop(frame_id, None)
+        if positions is not None:
+            p = np.asarray(positions)
+            if p.size == 0:
+                p = np.empty((0, 2), np.int32)
+            if p.ndim != 2 or p.shape[1] != 2 or p.shape[0] != t.shape[0]:
+                raise MatcherError(f"positions: expected [{t.shape[0]}, 2], got {p.shape}")
+            with torch.cuda.device(self.device):
+                self._points[frame_id] = torch.from_numpy(np.ascontiguousarray(p.astype(np.int32))).to(self.device)
         while len(self._frames) > self.capacity:
-            self._frames.popitem(last=False)
+            old, _ = self._frames.popitem(last=False)
+            self._points.pop(old, None)
         return t
 
     def get(self, frame_id) -> torch.Tensor:
@@ -141,6 +154,24 @@ class FrameDescriptorStore:
         packed = torch.cat([cnt.view(1), oq.view(-1), ot.view(-1), od.view(-1)]).cpu().numpy()
         n, nq = int(packed[0]), q.shape[0]
         return packed[1:1 + n].copy(), packed[1 + nq:1 + nq + n].copy(), packed[1 + 2 * nq:1 + 2 * nq + n].copy()
+
+    def matched_points(self, last_id, current_id, dist_threshold: Optional[float] = None):
+        """``(source_pts, query_pts)``, two packed ``(M, 2) int32`` arrays: the inputs `utils.py:13-19` and
+        `:41-47` build for ``cv2.findEssentialMat`` / ``triangulatePoints`` with a Python loop over the matches
+        (source = last frame = train side).  Matching, filtering and the gather (``hm_gather_points``) run on the
+        device; one D2H brings back the count and both arrays -- no DMatch objects, no index arrays."""
+        t, q = self._frames[last_id], self._frames[current_id]
+        if last_id not in self._points or current_id not in self._points:
+            raise MatcherError("matched_points needs both frames stored with positions")
+        if q.shape[0] == 0 or t.shape[0] == 0:
+            e = np.empty((0, 2), np.int32)
+            return e, e.copy()
+        oq, ot, _, cnt = nat.match_fused(q.unsqueeze(0), t.unsqueeze(0), ratio=self.ratio, cross_check=self.cross_check,
+                                         dist_threshold=dist_threshold if dist_threshold else None, variant=self.variant)
+        pq, pt = nat.gather_points(oq, ot, cnt, self._points[current_id].unsqueeze(0), self._points[last_id].unsqueeze(0))
+        packed = torch.cat([cnt.view(1), pq.view(-1), pt.view(-1)]).cpu().numpy()
+        n, nq = int(packed[0]), q.shape[0]
+        return packed[1 + 2 * nq:1 + 2 * nq + 2 * n].reshape(n, 2).copy(), packed[1:1 + 2 * n].reshape(n, 2).copy()
 
     def match(self, last_id, current_id, dist_threshold: Optional[float] = None):
         """DMatch sequence with the reference's return convention (tuple, or list when filtered)."""

@@ -113,3 +113,39 @@ def test_dropin_through_the_call_site_and_resident_store():
         pipe.put(0, g["train"]); pipe.put(1, g["query"])
         q, t, d = pipe.match_tensors(0, 1)
         assert np.array_equal(np.stack([q, t, d], 1), g["pipe75"][:, [0, 1, 3]])
+
+
+@pytest.mark.gpu
+def test_matched_points_gathered_on_device():
+    """8f rank 2: the point lists of `utils.py:13-19` / `:41-47` (a Python loop over DMatch objects in the
+    reference) come back as two packed arrays gathered on the device, for the plain matcher and the pipeline."""
+    rng = np.random.default_rng(3)
+    for name in ("c1_orb200.npz", "c1_orb2000.npz"):
+        g = load_golden(golden_files(name)[0])
+        last, cur = Frame(g["train"], 1), Frame(g["query"], 2)
+        pos_last, pos_cur = sx.keypoint_array(last.features), sx.keypoint_array(cur.features)
+        for kwargs, dist_thr in (({}, None), ({}, 30.0), ({"ratio": 0.75, "cross_check": True}, None)):
+            store = sx.FrameDescriptorStore(**kwargs)
+            store.put("last", last.get_descriptors(), pos_last)
+            store.put("cur", cur.get_descriptors(), pos_cur)
+            sp, qp = store.matched_points("last", "cur", dist_thr)
+            matches = store.match("last", "cur", dist_thr)                       # same matches as DMatch objects
+            ref_s = np.array([last.features[m.trainIdx].position for m in matches]).reshape(-1, 2)
+            ref_q = np.array([cur.features[m.queryIdx].position for m in matches]).reshape(-1, 2)
+            assert sp.dtype == np.int32 and np.array_equal(sp, ref_s) and np.array_equal(qp, ref_q)
+        store.put("none", np.array([]), np.empty((0, 2)))
+        sp, qp = store.matched_points("last", "none")
+        assert sp.shape == (0, 2) and qp.shape == (0, 2)
+        store.put("nopos", g["query"])
+        with pytest.raises(cv2.error):
+            store.matched_points("last", "nopos")
+    # raw kernel, batched, random indices
+    b, nq, nt = 3, 500, 700
+    q_idx = torch.from_numpy(rng.integers(0, nq, (b, nq)).astype(np.int32)).cuda()
+    t_idx = torch.from_numpy(rng.integers(0, nt, (b, nq)).astype(np.int32)).cuda()
+    cnt = torch.tensor([nq, 0, 123], dtype=torch.int32).cuda()
+    qp = torch.from_numpy(rng.integers(-5, 2000, (b, nq, 2)).astype(np.int32)).cuda()
+    tp = torch.from_numpy(rng.integers(-5, 2000, (b, nt, 2)).astype(np.int32)).cuda()
+    oq, ot = sx._native.gather_points(q_idx, t_idx, cnt, qp, tp)
+    for i, n in enumerate(cnt.tolist()):
+        assert torch.equal(oq[i, :n], qp[i][q_idx[i, :n].long()]) and torch.equal(ot[i, :n], tp[i][t_idx[i, :n].long()])
