@@ -201,6 +201,13 @@ HM_API int hm_gather_points(const int32_t* q_idx, const int32_t* t_idx, const in
                             const int32_t* query_pts, int64_t nq, const int32_t* train_pts, int64_t nt,
                             int32_t* out_query_pts, int32_t* out_train_pts, void* stream);
 
+/* ---- detection mask: replaces /root/reference/utils.py:58-74 (get_featured_detection_mask) ----------
+ * mask[h][w] (uint8, rows `row_stride` bytes apart) = inner ? 0 : 255 everywhere, then for each of the n
+ * points (x, y int32 pairs, 8-byte aligned) the filled rectangle [x-radius, x+radius] x [y-radius, y+radius]
+ * (inclusive, clipped to the image, like cv2.rectangle(..., cv2.FILLED)) = inner ? 255 : 0. */
+HM_API int hm_rasterize_mask(const int32_t* points, int64_t n, int radius, int inner,
+                             uint8_t* mask, int h, int w, int64_t row_stride, void* stream);
+
 /* ---- host-buffer convenience (what a non-torch caller binds) --------------------------- */
 typedef struct hm_context hm_context; /* owns a stream, device scratch and pinned staging */
 HM_API int hm_context_create(hm_context** out_ctx);

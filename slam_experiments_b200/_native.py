@@ -32,7 +32,7 @@ PREPARED_ROW_BYTES = {VARIANT_I8: 256, VARIANT_F4: 128}
 EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
     "hm_knn2", "hm_knn2_batched", "hm_default_tensor_variant", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials", "hm_knn2_prepared_exchange",
-    "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused", "hm_gather_points",
+    "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused", "hm_gather_points", "hm_rasterize_mask",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host",
 )
 
@@ -87,6 +87,8 @@ def _declare(L):
                                  vp, vp, vp, vp, vp, ci, vp, sz, vp]
     L.hm_gather_points.restype = ci
     L.hm_gather_points.argtypes = [vp, vp, vp, i64, ci, vp, i64, vp, i64, vp, vp, vp]
+    L.hm_rasterize_mask.restype = ci
+    L.hm_rasterize_mask.argtypes = [vp, i64, ci, ci, vp, ci, ci, i64, vp]
     L.hm_context_create.restype = ci
     L.hm_context_create.argtypes = [c.POINTER(vp)]
     L.hm_context_destroy.restype = None
@@ -409,6 +411,22 @@ def gather_points(q_idx: torch.Tensor, t_idx: torch.Tensor, count: torch.Tensor,
                                      query_pts.data_ptr(), query_pts.shape[1], train_pts.data_ptr(), train_pts.shape[1],
                                      oq.data_ptr(), ot.data_ptr(), _stream_ptr(dev)), "hm_gather_points")
     return oq, ot
+
+
+def rasterize_mask(points: torch.Tensor, shape, radius: int, inner: bool = True,
+                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``hm_rasterize_mask``: the detection mask of `utils.py:58-74` as a ``[h, w] uint8`` CUDA tensor;
+    ``points`` is a contiguous CUDA int32 ``[N, 2]`` tensor of (x, y) pixel positions."""
+    if points.dtype != torch.int32 or points.dim() != 2 or points.shape[1] != 2 or not points.is_cuda or not points.is_contiguous():
+        raise ValueError("points must be a contiguous CUDA int32 tensor [N, 2]")
+    h, w = int(shape[0]), int(shape[1])
+    dev = points.device
+    if out is None:
+        out = torch.empty((h, w), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        check(lib().hm_rasterize_mask(points.data_ptr(), points.shape[0], int(radius), 1 if inner else 0,
+                                      out.data_ptr(), h, w, out.stride(0) if h else w, _stream_ptr(dev)), "hm_rasterize_mask")
+    return out
 
 
 def profile_events(start: Optional[torch.cuda.Event], stop: Optional[torch.cuda.Event]) -> None:

@@ -489,6 +489,20 @@ HM_API int hm_gather_points(const int32_t* q_idx, const int32_t* t_idx, const in
                                 out_train_pts, static_cast<cudaStream_t>(stream));
 }
 
+HM_API int hm_rasterize_mask(const int32_t* points, int64_t n, int radius, int inner, uint8_t* mask, int h, int w,
+                             int64_t row_stride, void* stream)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (h < 0 || w < 0 || n < 0 || radius < 0 || ((h > 0 && w > 0) && (!mask || row_stride < w)) ||
+        (n > 0 && (!points || (reinterpret_cast<uintptr_t>(points) & 7)))) {
+        set_error("hm_rasterize_mask: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    return launch_rasterize_mask(points, n, radius, inner, mask, h, w, row_stride, static_cast<cudaStream_t>(stream));
+}
+
 // ---- host-buffer convenience ---------------------------------------------------------------
 struct hm_context {
     cudaStream_t stream;

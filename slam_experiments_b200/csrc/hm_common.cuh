@@ -229,4 +229,7 @@ int launch_gather_points(const int* q_idx, const int* t_idx, const int* count, l
                          const int* query_pts, long long nq, const int* train_pts, long long nt, int* out_query,
                          int* out_train, cudaStream_t stream);
 
+int launch_rasterize_mask(const int* pts, long long n, int radius, int inner, unsigned char* mask, int h, int w,
+                          long long row_stride, cudaStream_t stream);
+
 }  // namespace hm

@@ -259,4 +259,56 @@ int launch_gather_points(const int* q_idx, const int* t_idx, const int* count, l
     return HM_OK;
 }
 
+// ---- detection mask --------------------------------------------------------------
+// /root/reference/utils.py:58-74: mask = full(shape, inner ? 0 : 255); for every feature
+// cv2.rectangle(mask, pt - r, pt + r, inner ? 255 : 0, FILLED) -- inclusive corners, clipped to the image.
+// All rectangles write the same value, so the result does not depend on the order: one warp per feature,
+// after one fill.  HBM-bound on the fill (h * w bytes); the rectangles touch n * (2r+1)^2 bytes.
+struct MaskParams {
+    const int2* pts;
+    long long n;
+    int radius, h, w;
+    long long row_stride;
+    unsigned char* mask;
+    unsigned char value;
+};
+
+__global__ void __launch_bounds__(256) hm_mask_fill_kernel(unsigned char* mask, int h, int w, long long row_stride, unsigned char v)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)h * w) return;
+    mask[(i / w) * row_stride + (i % w)] = v;
+}
+
+__global__ void __launch_bounds__(256) hm_mask_rect_kernel(const MaskParams P)
+{
+    const long long f = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (f >= P.n) return;
+    const int lane = threadIdx.x & 31;
+    const int2 p = P.pts[f];
+    // 64-bit corners: positions near INT_MAX must clip, not wrap
+    const long long x0 = max((long long)p.x - P.radius, 0ll), x1 = min((long long)p.x + P.radius, (long long)P.w - 1);
+    const long long y0 = max((long long)p.y - P.radius, 0ll), y1 = min((long long)p.y + P.radius, (long long)P.h - 1);
+    if (x0 > x1 || y0 > y1) return;
+    const long long wd = x1 - x0 + 1, cells = wd * (y1 - y0 + 1);
+    for (long long c = lane; c < cells; c += 32) P.mask[(y0 + c / wd) * P.row_stride + x0 + c % wd] = P.value;
+}
+
+int launch_rasterize_mask(const int* pts, long long n, int radius, int inner, unsigned char* mask, int h, int w,
+                          long long row_stride, cudaStream_t stream)
+{
+    if (h <= 0 || w <= 0) return HM_OK;
+    const long long cells = (long long)h * w;
+    hm_mask_fill_kernel<<<(unsigned)ceil_div(cells, 256), 256, 0, stream>>>(mask, h, w, row_stride, inner ? 0 : 255);
+    HM_CUDA_CHECK(cudaGetLastError());
+    if (n > 0) {
+        MaskParams P{};
+        P.pts = reinterpret_cast<const int2*>(pts); P.n = n; P.radius = radius; P.h = h; P.w = w;
+        P.row_stride = row_stride; P.mask = mask; P.value = inner ? 255 : 0;
+        hm_mask_rect_kernel<<<(unsigned)ceil_div(n, 8), 256, 0, stream>>>(P);
+        HM_CUDA_CHECK(cudaGetLastError());
+    }
+    return HM_OK;
+}
+
 }  // namespace hm

@@ -77,6 +77,24 @@ def matched_point_arrays(q_idx: np.ndarray, t_idx: np.ndarray, source_positions:
     return source_positions[np.asarray(t_idx)], query_positions[np.asarray(q_idx)]
 
 
+def get_featured_detection_mask(shape, features_or_positions, radius: int, inner: bool = True, device=None) -> np.ndarray:
+    """``utils.get_featured_detection_mask`` (`utils.py:58-74`): a ``shape`` uint8 mask, 0 (``inner``) or 255
+    everywhere, with the filled square of half-width ``radius`` around every feature set to 255 / 0.  The
+    reference draws the squares with one ``cv2.rectangle`` call per feature from Python; here the positions
+    (``Feature.position`` of each feature, or an ``[N, 2]`` array -- e.g. the re-projected map points of the
+    reference's ``camera`` branch, computed by the caller) are rasterised by ``hm_rasterize_mask``."""
+    dev = nat.require_cuda(device)
+    if isinstance(features_or_positions, np.ndarray):
+        pos = features_or_positions.reshape(-1, 2).astype(np.int32)
+    elif len(features_or_positions) == 0:
+        pos = np.empty((0, 2), np.int32)
+    else:
+        pos = np.array([f.position for f in features_or_positions], dtype=np.int32).reshape(-1, 2)
+    with torch.cuda.device(dev):
+        pts = torch.from_numpy(np.ascontiguousarray(pos)).to(dev)
+        return nat.rasterize_mask(pts, shape, radius, inner).cpu().numpy()
+
+
 class FrameDescriptorStore:
     """Device-resident descriptors of recent frames.
 

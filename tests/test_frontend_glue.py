@@ -149,3 +149,31 @@ def test_matched_points_gathered_on_device():
     oq, ot = sx._native.gather_points(q_idx, t_idx, cnt, qp, tp)
     for i, n in enumerate(cnt.tolist()):
         assert torch.equal(oq[i, :n], qp[i][q_idx[i, :n].long()]) and torch.equal(ot[i, :n], tp[i][t_idx[i, :n].long()])
+
+
+@pytest.mark.gpu
+def test_detection_mask_equals_cv2_rectangles():
+    """8f rank 4: `utils.get_featured_detection_mask` (`utils.py:58-74`), one cv2.rectangle per feature in the
+    reference, rasterised on the device -- identical masks, borders and out-of-image points included."""
+    rng = np.random.default_rng(11)
+
+    def reference(shape, pos, radius, inner):              # utils.py:66-74 on Feature.position arrays
+        mask = np.full(shape, fill_value=0 if inner else 255, dtype=np.uint8)
+        shift = np.array([radius, radius])
+        for pt in pos:
+            mask = cv2.rectangle(mask, pt - shift, pt + shift, 255 if inner else 0, cv2.FILLED)
+        return mask
+
+    for shape, n, radius in (((480, 752), 2000, 10), ((480, 640), 200, 10), ((33, 47), 40, 3), ((5, 9), 6, 0), ((64, 64), 0, 4)):
+        pos = np.stack([rng.integers(-15, shape[1] + 15, n), rng.integers(-15, shape[0] + 15, n)], 1).astype(np.int32)
+        if n:
+            pos[0] = (0, 0); pos[-1] = (shape[1] - 1, shape[0] - 1)          # corners
+        for inner in (True, False):
+            got = sx.get_featured_detection_mask(shape, pos, radius, inner)
+            assert got.dtype == np.uint8 and got.shape == shape
+            assert np.array_equal(got, reference(shape, pos, radius, inner)), (shape, n, radius, inner)
+    # through Feature objects, as the frontend calls it (frontend.py:236-243)
+    g = load_golden(golden_files("c1_orb200.npz")[0])
+    fr = Frame(g["train"], 5)
+    pos = np.array([f.position for f in fr.features])
+    assert np.array_equal(sx.get_featured_detection_mask((480, 640), fr.features, 10, True), reference((480, 640), pos, 10, True))
