@@ -225,6 +225,23 @@ HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
                          unsigned flags, const uint16_t* ratio_lut_host, double dist_threshold, int variant,
                          int32_t* out_q_host, int32_t* out_t_host, int32_t* out_d_host, int32_t* out_count_host);
 
+/* ---- resident frames (SURVEY.md 8f ranks 1 + 2): replaces the per-call repacking of
+ *      /root/reference/primitives.py:200-205 + frontend.py:181-187 and the point loops of utils.py:13-19 ---- */
+#define HM_FRAME_SLOTS 16
+/* Upload a frame ONCE into `slot` (0 .. HM_FRAME_SLOTS-1) of the context: n descriptors (rows `stride` bytes
+ * apart) and, when points_host != NULL, its n keypoint positions (x, y int32 pairs).  Asynchronous; later
+ * calls on the context are ordered after it. */
+HM_API int hm_frame_put(hm_context* ctx, int slot, const uint8_t* desc_host, int64_t n, int64_t stride,
+                        const int32_t* points_host);
+/* hm_match_host between two resident frames (query = current frame, train = last frame).  Outputs as
+ * hm_match_host; out_q/out_t/out_d may be NULL.  When both out_*_pts_host are non-NULL (each [nq][2] int32)
+ * they receive the matched keypoint positions, gathered on the device: [m] = position of the query / train
+ * feature of match m -- the arrays utils.py:13-19 builds for cv2.findEssentialMat. */
+HM_API int hm_frame_match(hm_context* ctx, int train_slot, int query_slot, unsigned flags,
+                          const uint16_t* ratio_lut_host, double dist_threshold, int variant,
+                          int32_t* out_q_host, int32_t* out_t_host, int32_t* out_d_host,
+                          int32_t* out_query_pts_host, int32_t* out_train_pts_host, int32_t* out_count_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -33,7 +33,7 @@ EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
     "hm_knn2", "hm_knn2_batched", "hm_default_tensor_variant", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials", "hm_knn2_prepared_exchange",
     "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused", "hm_gather_points", "hm_rasterize_mask",
-    "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host",
+    "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host", "hm_frame_put", "hm_frame_match",
 )
 
 
@@ -95,6 +95,10 @@ def _declare(L):
     L.hm_context_destroy.argtypes = [vp]
     L.hm_knn2_host.restype = ci
     L.hm_knn2_host.argtypes = [vp, vp, i64, vp, i64, vp, ci]
+    L.hm_frame_put.restype = ci
+    L.hm_frame_put.argtypes = [vp, ci, vp, i64, i64, vp]
+    L.hm_frame_match.restype = ci
+    L.hm_frame_match.argtypes = [vp, ci, ci, cu, vp, c.c_double, ci, vp, vp, vp, vp, vp, vp]
     L.hm_match_host.restype = ci
     L.hm_match_host.argtypes = [vp, vp, i64, i64, vp, i64, i64, cu, vp, c.c_double, ci, vp, vp, vp, vp]
 
@@ -527,6 +531,52 @@ class HostContext:
                                   out[2].ctypes.data, ctypes.byref(cnt)), "hm_match_host")
         n = cnt.value
         return out[0, :n], out[1, :n], out[2, :n]
+
+    # ---- resident frames (hm_frame_put / hm_frame_match) ----
+    FRAME_SLOTS = 16
+
+    def frame_put(self, slot: int, descriptors: np.ndarray, positions: Optional[np.ndarray] = None) -> None:
+        d = descriptors
+        if d.shape[0] and (d.strides[1] != 1 or d.strides[0] < DESC_BYTES):
+            d = np.ascontiguousarray(d)
+        p_ptr = None
+        if positions is not None:
+            positions = np.ascontiguousarray(positions, dtype=np.int32)
+            p_ptr = positions.ctypes.data
+        check(lib().hm_frame_put(self._h, slot, d.ctypes.data if d.shape[0] else None, d.shape[0],
+                                 d.strides[0] if d.shape[0] else DESC_BYTES, p_ptr), "hm_frame_put")
+
+    def frame_match(self, train_slot: int, query_slot: int, nq: int, ratio: Optional[float] = None,
+                    cross_check: bool = False, dist_threshold: Optional[float] = None, variant="auto",
+                    want_indices: bool = True, want_points: bool = False):
+        """Match two resident frames.  Returns ``(q, t, d)`` int32 arrays and/or ``(query_pts, train_pts)``
+        ``(M, 2)`` int32 arrays, depending on ``want_indices`` / ``want_points``."""
+        flags, lut_ptr, lut, thr = 0, None, None, 0.0
+        if ratio is not None:
+            flags |= FLAG_RATIO
+            lut = _ratio_lut_cached(float(ratio))
+            lut_ptr = lut.ctypes.data
+        if cross_check:
+            flags |= FLAG_MUTUAL
+        if dist_threshold:
+            flags |= FLAG_DIST_THRESHOLD
+            thr = float(dist_threshold)
+        m = max(nq, 1)
+        idx = np.empty((3, m), dtype=np.int32) if want_indices else None
+        pts = np.empty((2, m, 2), dtype=np.int32) if want_points else None
+        cnt = ctypes.c_int32(0)
+        check(lib().hm_frame_match(self._h, train_slot, query_slot, flags, lut_ptr, thr, variant_id(variant),
+                                   idx[0].ctypes.data if want_indices else None, idx[1].ctypes.data if want_indices else None,
+                                   idx[2].ctypes.data if want_indices else None,
+                                   pts[0].ctypes.data if want_points else None, pts[1].ctypes.data if want_points else None,
+                                   ctypes.byref(cnt)), "hm_frame_match")
+        n = cnt.value
+        out = ()
+        if want_indices:
+            out += (idx[0, :n], idx[1, :n], idx[2, :n])
+        if want_points:
+            out += (pts[0, :n], pts[1, :n])
+        return out
 
     def close(self):
         if self._h:

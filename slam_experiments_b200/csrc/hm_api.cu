@@ -504,12 +504,25 @@ HM_API int hm_rasterize_mask(const int32_t* points, int64_t n, int radius, int i
 }
 
 // ---- host-buffer convenience ---------------------------------------------------------------
+constexpr int kFrameSlots = HM_FRAME_SLOTS;
+
+struct FrameSlot {
+    uint8_t* d;          // device: [descriptors n x 32 | pad | positions n x 2 int32]
+    size_t cap;
+    int64_t n;
+    bool has_points;
+    uint8_t* h;          // pinned staging of this slot, same carving
+    size_t h_cap;
+    cudaEvent_t uploaded;   // the last H2D out of `h` (the next put into this slot waits for it)
+};
+
 struct hm_context {
     cudaStream_t stream;
     uint8_t* d_buf;      // device: [query | train | keys | workspace]
     size_t d_cap;
     uint8_t* h_buf;      // pinned staging, same carving for query | train | keys
     size_t h_cap;
+    FrameSlot slots[kFrameSlots];   // resident frames (hm_frame_put / hm_frame_match)
 };
 
 HM_API int hm_context_create(hm_context** out_ctx)
@@ -540,6 +553,11 @@ HM_API int hm_context_create(hm_context** out_ctx)
 HM_API void hm_context_destroy(hm_context* ctx)
 {
     if (!ctx) return;
+    for (FrameSlot& f : ctx->slots) {
+        if (f.d) cudaFree(f.d);
+        if (f.h) cudaFreeHost(f.h);
+        if (f.uploaded) cudaEventDestroy(f.uploaded);
+    }
     if (ctx->d_buf) cudaFree(ctx->d_buf);
     if (ctx->h_buf) cudaFreeHost(ctx->h_buf);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -648,6 +666,107 @@ HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
     memcpy(out_q_host, h_q, (size_t)n * 4);
     memcpy(out_t_host, h_q + nq, (size_t)n * 4);
     memcpy(out_d_host, h_q + 2 * nq, (size_t)n * 4);
+    *out_count_host = n;
+    return HM_OK;
+}
+
+// ---- resident frames behind the context (SURVEY.md 8f ranks 1 + 2) --------------------------------------
+// The reference repacks and hands BOTH frames to the matcher on every call (frontend.py:181-187,
+// primitives.py:200-205).  Here a frame is uploaded once into a slot -- descriptors and, optionally, its
+// keypoint positions -- and a later call matches two resident slots: per tracking step only the new frame
+// crosses PCIe, and the matched point arrays of utils.py:13-19 / :41-47 come back gathered.
+static inline size_t slot_points_offset(int64_t n) { return align_up((size_t)n * HM_DESC_BYTES, 256); }
+
+HM_API int hm_frame_put(hm_context* ctx, int slot, const uint8_t* desc_host, int64_t n, int64_t stride,
+                        const int32_t* points_host)
+{
+    if (!ctx || slot < 0 || slot >= kFrameSlots || n < 0 || (n > 0 && (!desc_host || stride < HM_DESC_BYTES))) {
+        set_error("hm_frame_put: bad arguments (slots 0..%d)", kFrameSlots - 1);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    FrameSlot& f = ctx->slots[slot];
+    f.n = n;
+    f.has_points = points_host != nullptr;
+    if (n == 0) return HM_OK;
+    const size_t bytes = slot_points_offset(n) + (size_t)n * 8;
+    if (f.cap < bytes) {
+        HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));        // kernels may still read the old buffer
+        if (f.d) cudaFree(f.d);
+        if (f.h) cudaFreeHost(f.h);
+        f.d = f.h = nullptr; f.cap = f.h_cap = 0;
+        HM_CUDA_CHECK(cudaMalloc(&f.d, bytes + bytes / 2));
+        HM_CUDA_CHECK(cudaMallocHost(&f.h, bytes + bytes / 2));
+        f.cap = f.h_cap = bytes + bytes / 2;
+    }
+    if (!f.uploaded) HM_CUDA_CHECK(cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
+    else HM_CUDA_CHECK(cudaEventSynchronize(f.uploaded));          // the previous copy has left the staging buffer
+    copy_rows(f.h, desc_host, n, stride);
+    size_t copy_bytes = (size_t)n * HM_DESC_BYTES;
+    if (points_host) {
+        memcpy(f.h + slot_points_offset(n), points_host, (size_t)n * 8);
+        copy_bytes = bytes;
+    }
+    // stream order also keeps earlier matches that read this slot ahead of the overwrite
+    HM_CUDA_CHECK(cudaMemcpyAsync(f.d, f.h, copy_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    HM_CUDA_CHECK(cudaEventRecord(f.uploaded, ctx->stream));
+    return HM_OK;
+}
+
+HM_API int hm_frame_match(hm_context* ctx, int train_slot, int query_slot, unsigned flags, const uint16_t* ratio_lut_host,
+                          double dist_threshold, int variant, int32_t* out_q_host, int32_t* out_t_host,
+                          int32_t* out_d_host, int32_t* out_query_pts_host, int32_t* out_train_pts_host,
+                          int32_t* out_count_host)
+{
+    if (!ctx || train_slot < 0 || train_slot >= kFrameSlots || query_slot < 0 || query_slot >= kFrameSlots ||
+        !out_count_host) {
+        set_error("hm_frame_match: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    const FrameSlot& T = ctx->slots[train_slot];
+    const FrameSlot& Q = ctx->slots[query_slot];
+    const bool want_pts = out_query_pts_host && out_train_pts_host;
+    if (want_pts && (!T.has_points || !Q.has_points)) {
+        set_error("hm_frame_match: matched points requested but a frame was stored without positions");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    *out_count_host = 0;
+    const int64_t nq = Q.n, nt = T.n;
+    if (nq == 0 || nt == 0) return HM_OK;              // cv2: no matches when either side is empty
+    // result block: [count | pad][q][t][d][query pts][train pts], one D2H
+    const size_t rb = align_up(16 + (size_t)nq * 12 + (want_pts ? (size_t)nq * 16 : 0), 1024);
+    const size_t wsb = align_up(hm_workspace_bytes(nq, nt, 1, variant), 1024);
+    int rc = ctx_reserve(ctx, rb + wsb, rb);
+    if (rc != HM_OK) return rc;
+    uint8_t *dr = ctx->d_buf, *dw = dr + rb, *hr = ctx->h_buf;
+    int32_t* d_count = reinterpret_cast<int32_t*>(dr);
+    int32_t* d_q = reinterpret_cast<int32_t*>(dr + 16);
+    int32_t* d_t = d_q + nq;
+    int32_t* d_d = d_t + nq;
+    int32_t* d_pq = d_d + nq;          // 16 + 12 nq bytes: 8-byte aligned when nq is even; padded below otherwise
+    if (nq & 1) ++d_pq;
+    int32_t* d_pt = d_pq + 2 * nq;
+    rc = hm_match_fused(Q.d, nq, HM_DESC_BYTES, 0, T.d, nt, HM_DESC_BYTES, 0, 1, flags, ratio_lut_host, dist_threshold, d_q,
+                        d_t, d_d, d_count, nullptr, variant, dw, wsb, ctx->stream);
+    if (rc != HM_OK) return rc;
+    size_t out_bytes = 16 + (size_t)nq * 12;
+    if (want_pts) {
+        rc = hm_gather_points(d_q, d_t, d_count, nq, 1, reinterpret_cast<const int32_t*>(Q.d + slot_points_offset(nq)), nq,
+                              reinterpret_cast<const int32_t*>(T.d + slot_points_offset(nt)), nt, d_pq, d_pt, ctx->stream);
+        if (rc != HM_OK) return rc;
+        out_bytes = (size_t)(reinterpret_cast<uint8_t*>(d_pt + 2 * nq) - dr);
+    }
+    HM_CUDA_CHECK(cudaMemcpyAsync(hr, dr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    const int32_t n = *reinterpret_cast<int32_t*>(hr);
+    const int32_t* h_q = reinterpret_cast<int32_t*>(hr + 16);
+    if (out_q_host) memcpy(out_q_host, h_q, (size_t)n * 4);
+    if (out_t_host) memcpy(out_t_host, h_q + nq, (size_t)n * 4);
+    if (out_d_host) memcpy(out_d_host, h_q + 2 * nq, (size_t)n * 4);
+    if (want_pts) {
+        const int32_t* h_pq = h_q + 3 * nq + (nq & 1);
+        memcpy(out_query_pts_host, h_pq, (size_t)n * 8);
+        memcpy(out_train_pts_host, h_pq + 2 * nq, (size_t)n * 8);
+    }
     *out_count_host = n;
     return HM_OK;
 }

@@ -102,6 +102,10 @@ class FrameDescriptorStore:
     current_id)`` runs the fused pipeline on the two resident arrays -- no host repacking, no H2D for
     the train side.  Keeps at most ``capacity`` frames (oldest evicted), like the reference's 7 active
     keyframes (`backend.py:11`).
+
+    numpy frames live in the frame slots of an ``hm_context`` (``hm_frame_put`` / ``hm_frame_match``): one C
+    call per upload and one per match, nothing torch-level on the path.  Frames given as CUDA tensors stay
+    torch tensors and are matched through the device-pointer entry points.
     """
 
     def __init__(self, capacity: int = 8, *, ratio: Optional[float] = None, cross_check: bool = False,
@@ -112,12 +116,42 @@ class FrameDescriptorStore:
         self._frames: "OrderedDict[Any, torch.Tensor]" = OrderedDict()
         self._points: dict = {}                                   # frame_id -> [N, 2] int32 pixel positions on the device
         self._pin: Optional[torch.Tensor] = None
+        # numpy frames: frame_id -> (slot, rows, has_positions) in the C context
+        self._slots: "OrderedDict[Any, Tuple[int, int, bool]]" = OrderedDict()
+        self._free_slots = list(range(min(self.capacity, nat.HostContext.FRAME_SLOTS)))[::-1]
+        self._ctx: Optional[nat.HostContext] = None
 
     def __contains__(self, frame_id) -> bool:
-        return frame_id in self._frames
+        return frame_id in self._frames or frame_id in self._slots
 
     def __len__(self) -> int:
-        return len(self._frames)
+        return len(self._frames) + len(self._slots)
+
+    def _put_slot(self, frame_id, a: np.ndarray, positions) -> None:
+        if self._ctx is None:
+            with torch.cuda.device(self.device):
+                self._ctx = nat.HostContext()
+        if frame_id in self._slots:
+            slot = self._slots.pop(frame_id)[0]
+        else:
+            if not self._free_slots:                               # evict the oldest resident frame
+                _, (slot, _, _) = self._slots.popitem(last=False)
+            else:
+                slot = self._free_slots.pop()
+        pos = None
+        if positions is not None:
+            pos = np.asarray(positions)
+            if pos.size == 0:
+                pos = np.empty((0, 2), np.int32)
+            if pos.ndim != 2 or pos.shape[1] != 2 or pos.shape[0] != a.shape[0]:
+                raise MatcherError(f"positions: expected [{a.shape[0]}, 2], got {pos.shape}")
+            pos = pos.astype(np.int32, copy=False)
+        with torch.cuda.device(self.device):
+            self._ctx.frame_put(slot, a, pos)
+        self._slots[frame_id] = (slot, a.shape[0], pos is not None)
+        if frame_id in self._frames:
+            del self._frames[frame_id]
+            self._points.pop(frame_id, None)
 
     def put(self, frame_id, descriptors, positions=None) -> torch.Tensor:
         """Upload a frame once.  ``positions`` (optional ``[N, 2]`` pixel coordinates, truncated to int32 like
@@ -128,6 +162,9 @@ class FrameDescriptorStore:
                 a = np.empty((0, nat.DESC_BYTES), np.uint8)       # a frame without features
             if a.dtype != np.uint8 or a.ndim != 2 or a.shape[1] != nat.DESC_BYTES:
                 raise MatcherError(f"descriptors: expected uint8 [N, {nat.DESC_BYTES}], got {a.dtype} {a.shape}")
+            if len(self._free_slots) or len(self._slots):           # the C-context path (capacity <= 16 slots)
+                self._put_slot(frame_id, a, positions)
+                return None
             n = a.shape[0]
             with torch.cuda.device(self.device):
                 if n == 0:
@@ -161,8 +198,19 @@ class FrameDescriptorStore:
     def get(self, frame_id) -> torch.Tensor:
         return self._frames[frame_id]
 
+    def _slot_match(self, last_id, current_id, dist_threshold, want_indices, want_points):
+        (ts, nt, tp), (qs, nq, qp) = self._slots[last_id], self._slots[current_id]
+        if want_points and not (tp and qp):
+            raise MatcherError("matched_points needs both frames stored with positions")
+        with torch.cuda.device(self.device):
+            return self._ctx.frame_match(ts, qs, nq, ratio=self.ratio, cross_check=self.cross_check,
+                                         dist_threshold=dist_threshold if dist_threshold else None, variant=self.variant,
+                                         want_indices=want_indices, want_points=want_points)
+
     def match_tensors(self, last_id, current_id, dist_threshold: Optional[float] = None):
         """``(queryIdx, trainIdx, distance)`` int32 arrays; query = current frame, train = last frame."""
+        if last_id in self._slots and current_id in self._slots:
+            return self._slot_match(last_id, current_id, dist_threshold, True, False)
         t, q = self._frames[last_id], self._frames[current_id]
         if q.shape[0] == 0 or t.shape[0] == 0:
             e = np.empty(0, np.int32)
@@ -178,6 +226,9 @@ class FrameDescriptorStore:
         `:41-47` build for ``cv2.findEssentialMat`` / ``triangulatePoints`` with a Python loop over the matches
         (source = last frame = train side).  Matching, filtering and the gather (``hm_gather_points``) run on the
         device; one D2H brings back the count and both arrays -- no DMatch objects, no index arrays."""
+        if last_id in self._slots and current_id in self._slots:
+            qp, tp = self._slot_match(last_id, current_id, dist_threshold, False, True)
+            return tp, qp
         t, q = self._frames[last_id], self._frames[current_id]
         if last_id not in self._points or current_id not in self._points:
             raise MatcherError("matched_points needs both frames stored with positions")
