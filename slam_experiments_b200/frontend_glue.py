@@ -115,7 +115,6 @@ class FrameDescriptorStore:
         self.ratio, self.cross_check, self.variant = ratio, bool(cross_check), variant
         self._frames: "OrderedDict[Any, torch.Tensor]" = OrderedDict()
         self._points: dict = {}                                   # frame_id -> [N, 2] int32 pixel positions on the device
-        self._pin: Optional[torch.Tensor] = None
         # numpy frames: frame_id -> (slot, rows, has_positions) in the C context
         self._slots: "OrderedDict[Any, Tuple[int, int, bool]]" = OrderedDict()
         self._free_slots = list(range(min(self.capacity, nat.HostContext.FRAME_SLOTS)))[::-1]
@@ -162,23 +161,11 @@ class FrameDescriptorStore:
                 a = np.empty((0, nat.DESC_BYTES), np.uint8)       # a frame without features
             if a.dtype != np.uint8 or a.ndim != 2 or a.shape[1] != nat.DESC_BYTES:
                 raise MatcherError(f"descriptors: expected uint8 [N, {nat.DESC_BYTES}], got {a.dtype} {a.shape}")
-            if len(self._free_slots) or len(self._slots):           # the C-context path (capacity <= 16 slots)
-                self._put_slot(frame_id, a, positions)
-                return None
-            n = a.shape[0]
-            with torch.cuda.device(self.device):
-                if n == 0:
-                    t = torch.empty((0, nat.DESC_BYTES), dtype=torch.uint8, device=self.device)
-                else:
-                    nbytes = n * nat.DESC_BYTES
-                    if self._pin is None or self._pin.numel() < nbytes:
-                        self._pin = torch.empty(max(nbytes, 1 << 16), dtype=torch.uint8).pin_memory()
-                    host = self._pin[:nbytes].view(n, nat.DESC_BYTES)
-                    torch.cuda.current_stream(self.device).synchronize()   # the previous async copy has left the buffer
-                    host.numpy()[...] = a
-                    t = host.to(self.device, non_blocking=True)
-        else:
-            t = a.to(self.device).contiguous()
+            self._put_slot(frame_id, a, positions)                   # the C-context path (at most 16 resident frames)
+            return None
+        t = a.to(self.device).contiguous()
+        if frame_id in self._slots:
+            self._free_slots.append(self._slots.pop(frame_id)[0])
         self._frames[frame_id] = t
         self._frames.move_to_end(frame_id)
         self._points.pop(frame_id, None)

@@ -177,3 +177,20 @@ def test_detection_mask_equals_cv2_rectangles():
     fr = Frame(g["train"], 5)
     pos = np.array([f.position for f in fr.features])
     assert np.array_equal(sx.get_featured_detection_mask((480, 640), fr.features, 10, True), reference((480, 640), pos, 10, True))
+
+
+@pytest.mark.gpu
+def test_store_accepts_cuda_tensors():
+    """Frames that already live on the device (CUDA tensors) are matched through the device-pointer entry
+    points; same results as the numpy / frame-slot path."""
+    g = load_golden(golden_files("c1_orb500.npz")[0])
+    last, cur = Frame(g["train"], 1), Frame(g["query"], 2)
+    pos_last, pos_cur = sx.keypoint_array(last.features), sx.keypoint_array(cur.features)
+    a, b = sx.FrameDescriptorStore(ratio=0.8), sx.FrameDescriptorStore(ratio=0.8)
+    a.put(0, g["train"], pos_last); a.put(1, g["query"], pos_cur)
+    b.put(0, torch.from_numpy(g["train"]).cuda(), pos_last); b.put(1, torch.from_numpy(g["query"]).cuda(), pos_cur)
+    for x, y in zip(a.match_tensors(0, 1), b.match_tensors(0, 1)):
+        assert np.array_equal(x, y)
+    for x, y in zip(a.matched_points(0, 1), b.matched_points(0, 1)):
+        assert np.array_equal(x, y)
+    assert [(m.queryIdx, m.trainIdx) for m in a.match(0, 1)] == [(m.queryIdx, m.trainIdx) for m in b.match(0, 1)]

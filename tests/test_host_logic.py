@@ -111,3 +111,16 @@ def test_shard_ranges_tile_the_collection():
                 assert kf_lo <= kf_hi and row_lo == starts[kf_lo] and row_hi == starts[kf_hi]
     r = sx.shard_ranges([2000] * 4096, 8)
     assert all(hi - lo == 512 for lo, hi, _, _ in r)
+
+
+def test_locate_rows_equals_searchsorted():
+    """(imgIdx, trainIdx) decoding of global rows: the division fast path for equal-sized keyframes and the
+    binary search for ragged collections give cv2's collection indices."""
+    from slam_experiments_b200 import _native as nat
+    rng = np.random.default_rng(0)
+    for sizes in ([2000] * 64, [5, 7, 0, 3], [4, 4, 4, 5], [1], [3, 3], [0, 0, 9], [7] * 3 + [0]):
+        starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        g = rng.integers(0, starts[-1], (50, 2)).astype(np.int64)
+        img, loc = nat.locate_rows(starts, g)
+        e = np.searchsorted(starts, g, side="right") - 1
+        assert img.dtype == np.int32 and np.array_equal(img, e) and np.array_equal(loc, g - starts[e]), sizes[:4]
