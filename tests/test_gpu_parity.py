@@ -290,3 +290,18 @@ def test_split_launch_shared_row_thresholds(variant):
     # distances all above 128 (negative dot products): complement-like rows only
     t2 = (~q[rng.integers(0, nq, nt)]) ^ rng.integers(0, 2, (nt, 32), dtype=np.uint8)
     assert np.array_equal(gpu_keys(q, t2, variant), co.knn2_keys(q, t2))
+
+
+@pytest.mark.parametrize("variant", ("i8", "f4"))
+def test_batched_split_launch(variant):
+    """Several independent problems in one launch, each split over many CTAs per query row: the shared row
+    thresholds are indexed per (problem, row), and ragged sizes leave padding rows / columns in every tile."""
+    rng = np.random.default_rng(21)
+    b, nq, nt = 3, 333, 20011
+    q = rng.integers(0, 256, (b, nq, 32), dtype=np.uint8)
+    t = rng.integers(0, 4, (b, nt, 32), dtype=np.uint8)                 # low-entropy train rows: many ties
+    t[1] = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    q[2, :50] = t[2, rng.choice(nt, 50, replace=False)]                 # exact matches in problem 2 only
+    keys = nat.knn2_keys_batched(dev(q), dev(t), variant=variant).cpu().numpy().view(np.uint64)
+    for i in range(b):
+        assert np.array_equal(keys[i], co.knn2_keys(q[i], t[i])), i
