@@ -457,11 +457,15 @@ HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, in
     KnnProblem p{};
     p.q = query; p.t = train; p.nq = nq; p.nt = nt; p.q_stride = q_stride; p.t_stride = t_stride;
     p.q_batch_stride = q_batch_stride; p.t_batch_stride = t_batch_stride; p.batch = batch;
+    // cv2.BFMatcher.match() -- the reference's own call (feature_matchers.py:39) -- is k = 1: without the ratio
+    // test nobody reads the second neighbour
+    p.top1 = !(flags & HM_FLAG_RATIO) && !out_keys;
     if ((rc = knn2_dispatch(p, fwd, variant, knn_ws, knn_ws_bytes, st)) != HM_OK) return rc;
     if ((flags & HM_FLAG_MUTUAL) && nq > 0 && nt > 0) {
         KnnProblem r{};
         r.q = train; r.t = query; r.nq = nt; r.nt = nq; r.q_stride = t_stride; r.t_stride = q_stride;
         r.q_batch_stride = t_batch_stride; r.t_batch_stride = q_batch_stride; r.batch = batch;
+        r.top1 = true;                       // the filter only reads each train row's best query
         if ((rc = knn2_dispatch(r, bwd, variant, knn_ws, knn_ws_bytes, st)) != HM_OK) return rc;
     }
     if (!out_count || (nq > 0 && (!out_q || !out_t || !out_d))) {

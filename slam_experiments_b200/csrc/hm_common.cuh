@@ -33,6 +33,7 @@ struct KnnProblem {
     long long q_batch_stride, t_batch_stride; // bytes between problems
     int batch;
     unsigned long long train_base;            // added to every trainIdx
+    bool top1;                                // only the nearest neighbour is needed (second key may be HM_NO_MATCH)
 };
 
 struct DeviceInfo {

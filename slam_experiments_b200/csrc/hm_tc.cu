@@ -292,7 +292,10 @@ __device__ __forceinline__ void tmem_ld_fence64(uint32_t (&a)[64])
 // running second best decides whether anything can change the top-2.  Only then are the groups
 // revisited, and the exact (value, index) insertion runs for the groups that still qualify.
 // Strict '>' keeps the lowest train index on ties because columns are visited in ascending order.
-template <class C, bool kFloor, int kGroups = 4>
+// kMode: 0 = top-2, 1 = top-2 with the shared row threshold, 2 = top-1 only (the swapped pass of the mutual
+// check needs nothing else: the threshold is then the best dot itself, so the exact-insertion path fires
+// about half as often and is shorter)
+template <class C, int kMode, int kGroups = 4>
 __device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, unsigned limit,
                                            Top2<typename C::Acc>& s)
 {
@@ -306,16 +309,19 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, 
                         C::max2(C::from_bits(r[o + 6]), C::from_bits(r[o + 7])));
     }
     const Acc m = kGroups == 4 ? C::max3(gm[0], gm[1], C::max2(gm[2], gm[3])) : C::max2(gm[0], gm[1]);
-    if (m > (kFloor ? s.f : s.v2)) {
+    constexpr bool kFloor = kMode == 1, kTop1 = kMode == 2;
+    if (m > (kFloor ? s.f : kTop1 ? s.v1 : s.v2)) {
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) {
-            if (gm[g] > (kFloor ? s.f : s.v2)) {
+            if (gm[g] > (kFloor ? s.f : kTop1 ? s.v1 : s.v2)) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const Acc x = C::from_bits(r[g * 8 + e]);
                     const unsigned idx = colbase + g * 8 + e;
-                    if (x > (kFloor ? s.f : s.v2) && idx < limit) {
-                        if (x > s.v1) {
+                    if (x > (kFloor ? s.f : kTop1 ? s.v1 : s.v2) && idx < limit) {
+                        if (kTop1) {
+                            s.v1 = x;    s.i1 = idx;
+                        } else if (x > s.v1) {
                             s.v2 = s.v1; s.i2 = s.i1;
                             s.v1 = x;    s.i1 = idx;
                         } else {
@@ -347,9 +353,10 @@ __device__ __forceinline__ void issue_half(int h, uint32_t a_block, uint32_t b_s
     }
 }
 
-template <class C, bool kFloor>
+template <class C, int kMode>
 __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
 {
+    constexpr bool kFloor = kMode == 1;
     using Acc = typename C::Acc;
     constexpr int kStages = C::kStages;
     constexpr int kUnits = C::kUnits;
@@ -572,10 +579,10 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-                scan_chunk<C, kFloor>(r0, colbase, limit, s);
-                scan_chunk<C, kFloor>(r1, colbase + 32, limit, s);
-                scan_chunk<C, kFloor>(r2, colbase + 64, limit, s);
-                scan_chunk<C, kFloor>(r3, colbase + 96, limit, s);
+                scan_chunk<C, kMode>(r0, colbase, limit, s);
+                scan_chunk<C, kMode>(r1, colbase + 32, limit, s);
+                scan_chunk<C, kMode>(r2, colbase + 64, limit, s);
+                scan_chunk<C, kMode>(r3, colbase + 96, limit, s);
             } else {
                 if constexpr (kCols == 64) {
                     uint32_t r[64];
@@ -588,8 +595,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     // warp-uniform votes around the insertion path 871; software pipelining over half items -- two
                     // 32-register buffers, the next item's first half loaded while this item's second half is
                     // scanned -- 882)
-                    scan_chunk<C, kFloor>(r, colbase, limit, s);
-                    scan_chunk<C, kFloor>(r + 32, colbase + 32, limit, s);
+                    scan_chunk<C, kMode>(r, colbase, limit, s);
+                    scan_chunk<C, kMode>(r + 32, colbase + 32, limit, s);
                 } else {
                     static_assert(kCols == 64 || kCols == 48, "column split");
                     uint32_t r0[32], r1[16];
@@ -599,8 +606,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     ptx::tc_fence_before();
                     __syncwarp();
                     if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-                    scan_chunk<C, kFloor>(r0, colbase, limit, s);
-                    scan_chunk<C, kFloor, 2>(r1, colbase + 32, limit, s);
+                    scan_chunk<C, kMode>(r0, colbase, limit, s);
+                    scan_chunk<C, kMode, 2>(r1, colbase + 32, limit, s);
                 }
             }
             unit += 2;
@@ -609,7 +616,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         }
         const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
         my_keys.x = C::valid(s.v1) ? ((unsigned long long)C::distance(s.v1) << 32) | (gbase + s.i1) : kNoMatch;
-        my_keys.y = C::valid(s.v2) ? ((unsigned long long)C::distance(s.v2) << 32) | (gbase + s.i2) : kNoMatch;
+        my_keys.y = (kMode != 2 && C::valid(s.v2)) ? ((unsigned long long)C::distance(s.v2) << 32) | (gbase + s.i2) : kNoMatch;
         if (half == 1) handover[row_in_cta] = my_keys;    // merged by the warp of the lower column half below
         else my_row = row;
         my_row_in_cta = row_in_cta;
@@ -646,17 +653,20 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     }
 }
 
-__global__ void __launch_bounds__(threads<CoreI8>(), 1) hm_i8_knn2_kernel(const TcParams P) { tc_knn2_body<CoreI8, false>(P); }
-__global__ void __launch_bounds__(threads<CoreF4>(), 1) hm_f4_knn2_kernel(const TcParams P) { tc_knn2_body<CoreF4, false>(P); }
+__global__ void __launch_bounds__(threads<CoreI8>(), 1) hm_i8_knn2_kernel(const TcParams P) { tc_knn2_body<CoreI8, 0>(P); }
+__global__ void __launch_bounds__(threads<CoreF4>(), 1) hm_f4_knn2_kernel(const TcParams P) { tc_knn2_body<CoreF4, 0>(P); }
 // the same kernels with the shared row thresholds (TcParams::row_floor): launched when the train set is split
 // over many short CTAs per query row
-__global__ void __launch_bounds__(threads<CoreI8>(), 1) hm_i8_knn2_floor_kernel(const TcParams P) { tc_knn2_body<CoreI8, true>(P); }
-__global__ void __launch_bounds__(threads<CoreF4>(), 1) hm_f4_knn2_floor_kernel(const TcParams P) { tc_knn2_body<CoreF4, true>(P); }
+__global__ void __launch_bounds__(threads<CoreI8>(), 1) hm_i8_knn2_floor_kernel(const TcParams P) { tc_knn2_body<CoreI8, 1>(P); }
+__global__ void __launch_bounds__(threads<CoreF4>(), 1) hm_f4_knn2_floor_kernel(const TcParams P) { tc_knn2_body<CoreF4, 1>(P); }
+// nearest neighbour only (second key = HM_NO_MATCH): the swapped pass of the mutual check
+__global__ void __launch_bounds__(threads<CoreI8>(), 1) hm_i8_knn1_kernel(const TcParams P) { tc_knn2_body<CoreI8, 2>(P); }
+__global__ void __launch_bounds__(threads<CoreF4>(), 1) hm_f4_knn1_kernel(const TcParams P) { tc_knn2_body<CoreF4, 2>(P); }
 
 using KernelFn = void (*)(const TcParams);
-template <class C> KernelFn kernel_of(bool floor = false);
-template <> KernelFn kernel_of<CoreI8>(bool floor) { return floor ? hm_i8_knn2_floor_kernel : hm_i8_knn2_kernel; }
-template <> KernelFn kernel_of<CoreF4>(bool floor) { return floor ? hm_f4_knn2_floor_kernel : hm_f4_knn2_kernel; }
+template <class C> KernelFn kernel_of(int mode = 0);
+template <> KernelFn kernel_of<CoreI8>(int mode) { return mode == 1 ? hm_i8_knn2_floor_kernel : mode == 2 ? hm_i8_knn1_kernel : hm_i8_knn2_kernel; }
+template <> KernelFn kernel_of<CoreF4>(int mode) { return mode == 1 ? hm_f4_knn2_floor_kernel : mode == 2 ? hm_f4_knn1_kernel : hm_f4_knn2_kernel; }
 
 struct TcPlan {
     int ntiles, splits, tiles_per_split;
@@ -779,12 +789,12 @@ template <class C>
 int launch_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
                     unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
                     int sm_count, cudaStream_t stream, const unsigned long long** out_partials,
-                    int* out_groups, const ExchangeArgs* exchange)
+                    int* out_groups, const ExchangeArgs* exchange, bool top1 = false)
 {
     static bool attr_set = false;
     if (!attr_set) {
-        HM_CUDA_CHECK(cudaFuncSetAttribute(kernel_of<C>(false), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()));
-        HM_CUDA_CHECK(cudaFuncSetAttribute(kernel_of<C>(true), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()));
+        for (int mode = 0; mode < 3; ++mode)
+            HM_CUDA_CHECK(cudaFuncSetAttribute(kernel_of<C>(mode), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()));
         attr_set = true;
     }
     const TcPlan pl = plan_tc<C>(nq, nt, batch, sm_count);
@@ -838,7 +848,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
     if ((pl.splits > 1 || fused_exchange) && !keep_partials) {   // merge in-kernel: last CTA per query block writes `out`
         P.counters = counters;
         P.final_out = out;
-        if (pl.splits > 1 && pl.tiles_per_split <= floor_max_tiles())
+        if (pl.splits > 1 && pl.tiles_per_split <= floor_max_tiles() && !top1)
             P.row_floor = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(counters) + counters_bytes(pl.qblocks * batch));
         HM_CUDA_CHECK(cudaMemsetAsync(counters, 0, cbytes, stream));
     } else if (!(pl.splits > 1 || keep_partials)) {
@@ -862,7 +872,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     profile_mark(true, stream);
-    cudaError_t le = cudaLaunchKernelEx(&cfg, kernel_of<C>(P.row_floor != nullptr), P);
+    cudaError_t le = cudaLaunchKernelEx(&cfg, kernel_of<C>(P.row_floor ? 1 : top1 ? 2 : 0), P);
     profile_mark(false, stream);
     if (le != cudaSuccess) {
         set_error("cudaLaunchKernelEx(tensor-core k-NN kernel, cluster %d) failed: %s", pl.cluster, cudaGetErrorString(le));
@@ -926,7 +936,7 @@ int launch_knn2_of(const KnnProblem& p, unsigned long long* out, void* ws, size_
     rc = launch_prepare_of<C>(p.t, p.nt, p.t_stride, p.t_batch_stride, p.batch, tprep, stream);
     if (rc != HM_OK) return rc;
     return launch_prepared<C>(qprep, p.nq, tprep, p.nt, p.batch, p.train_base, out, ws, head, sm_count, stream, nullptr,
-                              nullptr, nullptr);
+                              nullptr, nullptr, p.top1);
 }
 
 }  // namespace
