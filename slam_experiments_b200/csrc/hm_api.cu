@@ -74,8 +74,8 @@ namespace {
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // Static per-shape table ("variant selection"): the tensor-core variant pays an
-// operand-expansion pre-pass and needs >= 128 query rows per CTA; below ~3e7 pairs the POPC
-// kernel (one launch, train split over the grid) is launch/latency-bound and wins.
+// operand-expansion pre-pass (two more launches, ~3 us each); kernel-only times (profiles/r02c_probe_shapes.txt):
+// 2000 x 2000 POPC 22 us vs tensor 15 + 6 us, 4096 x 4096 52 us vs 22 + 6 us -- crossover near 8e6 pairs.
 // The tensor-core core AUTO resolves to.  HM_TENSOR_CORE=i8|f4 overrides it for experiments.
 int default_tensor_variant()
 {
@@ -90,7 +90,7 @@ int default_tensor_variant()
 int select_variant(long long nq, long long nt, int batch)
 {
     const double pairs = (double)nq * (double)nt * (double)batch;
-    if (nq >= 64 && nt >= 256 && pairs >= 3.0e7) return default_tensor_variant();
+    if (nq >= 64 && nt >= 256 && pairs >= 8.0e6) return default_tensor_variant();
     return HM_VARIANT_POPC;
 }
 
