@@ -70,6 +70,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     ] + [os.path.join(CSRC, f) for f in SOURCES]
     if trace:      # pipeline-trace build of the tensor-core kernels
         cmd.insert(1, "-DHM_TC_TRACE=" + os.environ.get("HM_BUILD_TRACE_STAMPS", "1"))
+        if os.environ.get("HM_BUILD_DEFINE"):          # e.g. HM_BUILD_DEFINE=HM_SPIN_FULL -> libhm_matcher_HM_SPIN_FULL.so
+            cmd.insert(1, "-D" + os.environ["HM_BUILD_DEFINE"])
+            so = os.path.join(HERE, f"libhm_matcher_{os.environ['HM_BUILD_DEFINE'].split('=')[0]}.so")
+            cmd[cmd.index("-o") + 1] = so
         if os.environ.get("HM_BUILD_EXPERIMENT"):
             cmd.insert(1, "-DHM_TC_EXPERIMENT=" + os.environ["HM_BUILD_EXPERIMENT"])
             so = os.path.join(HERE, f"libhm_matcher_exp{os.environ['HM_BUILD_EXPERIMENT']}.so")
