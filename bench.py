@@ -4,7 +4,8 @@
 Default workload (BASELINE.json configs[3], the one quoted at 1/2/4/8 GPUs): the
 keyframe-database query -- 2000 query descriptors against 4096 keyframes x 2000 train
 descriptors (8,192,000 rows), the train set sharded across the N GPUs of one box by contiguous
-keyframe ranges, per-shard top-2 candidates merged after one NCCL all-gather.  A "step" is one
+keyframe ranges, per-shard top-2 candidates merged in one exchange step (peer stores over NVLink inside
+the k-NN kernel; `--exchange nccl` = all-gather + merge kernel).  A "step" is one
 query batch against the whole database.  `value` is whole-job Gpairs/s with the database and the
 query already resident in HBM; `e2e` is the same metric through the reference-facing drop-in
 (`ShardedKeyframeDatabase.knnMatch`, the cv2 collection API `bf.add(...); bf.knnMatch(q, k=2)`)

@@ -6,8 +6,10 @@ train-collection API, ``bf.add([kf0, kf1, ...]); bf.knnMatch(query, k=2)``, whos
 global stable top-k over the row concatenation reported as ``(imgIdx, trainIdx)``
 (SURVEY.md E5).  Here each rank (one process per GPU) keeps a contiguous range of keyframes
 resident, computes its local top-2 with global row ids, and the per-shard candidates are
-merged after ONE exchange step: an all-gather of ``Nq x 2`` packed 64-bit keys (32 KB per
-rank for 2000 queries) over NCCL / NVLink, followed by ``hm_merge_top2``.  Unsigned min over
+merged after ONE exchange step of ``Nq x 2`` packed 64-bit keys (32 KB per rank for 2000 queries):
+by default inside the k-NN kernel itself (``hm_knn2_prepared_exchange``: peer stores into symmetric
+memory over NVLink + epoch flags + merge by the last CTA of each query block), else an NCCL all-gather
+followed by ``hm_merge_top2``.  Unsigned min over
 ``(dist << 32 | global_row)`` is cv2's order because a lower global row is a lower
 ``(imgIdx, trainIdx)``.
 """

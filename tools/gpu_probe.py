@@ -1,4 +1,4 @@
-"""Quick device-side timing of both kernel variants over a few shapes (development aid)."""
+"""Device-side timing of the three kernel variants over a few shapes (development aid)."""
 import sys, os, json, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
