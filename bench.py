@@ -14,7 +14,7 @@ with the query in host memory and DMatch tuples out.
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     torchrun --nproc-per-node N bench.py --gpus N ...
 
-Other workloads (--workload c2|c3|c5) are single-GPU lines used for DESIGN.md / profiles.
+Other workloads (--workload c1|c2|c3|c5) are single-GPU lines used for DESIGN.md / profiles.
 """
 from __future__ import annotations
 
@@ -410,7 +410,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--variant", default="auto", choices=["auto", "popc", "i8", "f4"])
-    ap.add_argument("--workload", default="c4", choices=["c4", "c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c4", choices=["c4", "c1", "c2", "c3", "c5"])
     ap.add_argument("--n", type=int, default=65536, help="c3: N x N")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"])
     ap.add_argument("--no-verify", action="store_true")

@@ -520,7 +520,31 @@ struct FrameSlot {
     cudaEvent_t uploaded;   // the last H2D out of `h` (the next put into this slot waits for it)
 };
 
+// Small problems are bound by launch latency, not by the kernels (200 x 200: ~6 us of GPU work behind five
+// driver calls): the host-buffer entry points replay a CUDA graph of their whole stream sequence -- H2D,
+// memset, k-NN, filter, (gather,) D2H -- once a shape has been seen twice.
+struct GraphKey {
+    int kind;                        // 0 = hm_match_host, 1 = hm_frame_match
+    int64_t nq, nt;
+    unsigned flags;
+    int variant, want_pts, has_lut;
+    double thr;
+    const void* ptr[4];              // every buffer the captured sequence touches
+    uint16_t lut[257];
+};
+
+struct GraphEntry {
+    GraphKey key;
+    int uses;                        // calls seen with this key; -1 = capture failed, never try again
+    cudaGraphExec_t exec;
+};
+
+constexpr int kGraphCache = 12;
+constexpr double kGraphMaxPairs = 6.4e7;   // above this the launches are noise
+
 struct hm_context {
+    GraphEntry graphs[kGraphCache];
+    int graph_next;
     cudaStream_t stream;
     uint8_t* d_buf;      // device: [query | train | keys | workspace]
     size_t d_cap;
@@ -557,6 +581,8 @@ HM_API int hm_context_create(hm_context** out_ctx)
 HM_API void hm_context_destroy(hm_context* ctx)
 {
     if (!ctx) return;
+    for (GraphEntry& g : ctx->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     for (FrameSlot& f : ctx->slots) {
         if (f.d) cudaFree(f.d);
         if (f.h) cudaFreeHost(f.h);
@@ -567,6 +593,72 @@ HM_API void hm_context_destroy(hm_context* ctx)
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
+
+}  // extern "C"
+
+static bool same_key(const GraphKey& a, const GraphKey& b)
+{
+    return a.kind == b.kind && a.nq == b.nq && a.nt == b.nt && a.flags == b.flags && a.variant == b.variant &&
+           a.want_pts == b.want_pts && a.has_lut == b.has_lut && a.thr == b.thr &&
+           !memcmp(a.ptr, b.ptr, sizeof(a.ptr)) && (!a.has_lut || !memcmp(a.lut, b.lut, sizeof(a.lut)));
+}
+
+// Runs `enqueue()` (which only enqueues work on ctx->stream) directly the first time a key is seen, captures
+// it into a graph the second time, and replays the graph afterwards.
+template <class F>
+static int run_cached_graph(hm_context* ctx, const GraphKey& key, F&& enqueue)
+{
+    const bool eligible = (double)key.nq * (double)key.nt <= kGraphMaxPairs && !(g_prof_start && g_prof_stop) &&
+                          !getenv("HM_NO_GRAPHS");
+    if (!eligible) return enqueue();
+    GraphEntry* e = nullptr;
+    for (GraphEntry& g : ctx->graphs)
+        if (g.uses != 0 && same_key(g.key, key)) { e = &g; break; }
+    if (!e) {                                        // first sighting: run directly, remember the key
+        e = &ctx->graphs[ctx->graph_next];
+        ctx->graph_next = (ctx->graph_next + 1) % kGraphCache;
+        if (e->exec) cudaGraphExecDestroy(e->exec);
+        e->exec = nullptr;
+        e->key = key;
+        e->uses = 1;
+        return enqueue();
+    }
+    if (e->uses < 0) return enqueue();
+    if (!e->exec) {
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            e->uses = -1;
+            return enqueue();
+        }
+        const int rc = enqueue();
+        const cudaError_t ce = cudaStreamEndCapture(ctx->stream, &graph);
+        if (rc != HM_OK || ce != cudaSuccess || !graph ||
+            cudaGraphInstantiate(&e->exec, graph, 0) != cudaSuccess) {
+            cudaGetLastError();
+            if (graph) cudaGraphDestroy(graph);
+            e->exec = nullptr;
+            e->uses = -1;
+            return rc != HM_OK ? rc : enqueue();     // nothing ran during the failed capture
+        }
+        cudaGraphDestroy(graph);
+    }
+    ++e->uses;
+    HM_CUDA_CHECK(cudaGraphLaunch(e->exec, ctx->stream));
+    return HM_OK;
+}
+
+static void fill_key(GraphKey* k, int kind, int64_t nq, int64_t nt, unsigned flags, int variant, int want_pts,
+                     const uint16_t* lut, double thr)
+{
+    memset(k, 0, sizeof(*k));
+    k->kind = kind; k->nq = nq; k->nt = nt; k->flags = flags; k->variant = variant; k->want_pts = want_pts;
+    k->thr = (flags & HM_FLAG_DIST_THRESHOLD) ? thr : 0.0;
+    k->has_lut = (flags & HM_FLAG_RATIO) && lut;
+    if (k->has_lut) memcpy(k->lut, lut, sizeof(k->lut));
+}
+
+extern "C" {
 
 HM_API int hm_knn2_host(hm_context* ctx, const uint8_t* query_host, int64_t nq, const uint8_t* train_host, int64_t nt,
                         uint64_t* out_keys_host, int variant)
@@ -654,16 +746,23 @@ HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
     uint8_t *hq = ctx->h_buf, *ht = hq + qb, *hr = ht + tb;
     copy_rows(hq, query_host, nq, q_stride);
     copy_rows(ht, train_host, nt, t_stride);
-    // query and train staging are adjacent: one H2D covers both
-    HM_CUDA_CHECK(cudaMemcpyAsync(dq, hq, qb + (size_t)nt * HM_DESC_BYTES, cudaMemcpyHostToDevice, ctx->stream));
     int32_t* d_count = reinterpret_cast<int32_t*>(dr);
     int32_t* d_q = reinterpret_cast<int32_t*>(dr + 16);
     int32_t* d_t = d_q + nq;
     int32_t* d_d = d_t + nq;
-    rc = hm_match_fused(dq, nq, HM_DESC_BYTES, 0, dt, nt, HM_DESC_BYTES, 0, 1, flags, ratio_lut_host, dist_threshold, d_q,
-                        d_t, d_d, d_count, nullptr, variant, dw, wsb, ctx->stream);
+    GraphKey key;
+    fill_key(&key, 0, nq, nt, flags, variant, 0, ratio_lut_host, dist_threshold);
+    key.ptr[0] = ctx->d_buf; key.ptr[1] = ctx->h_buf;
+    rc = run_cached_graph(ctx, key, [&]() -> int {
+        // query and train staging are adjacent: one H2D covers both
+        HM_CUDA_CHECK(cudaMemcpyAsync(dq, hq, qb + (size_t)nt * HM_DESC_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+        const int r = hm_match_fused(dq, nq, HM_DESC_BYTES, 0, dt, nt, HM_DESC_BYTES, 0, 1, flags, ratio_lut_host,
+                                     dist_threshold, d_q, d_t, d_d, d_count, nullptr, variant, dw, wsb, ctx->stream);
+        if (r != HM_OK) return r;
+        HM_CUDA_CHECK(cudaMemcpyAsync(hr, dr, (size_t)nq * 12 + 16, cudaMemcpyDeviceToHost, ctx->stream));
+        return HM_OK;
+    });
     if (rc != HM_OK) return rc;
-    HM_CUDA_CHECK(cudaMemcpyAsync(hr, dr, (size_t)nq * 12 + 16, cudaMemcpyDeviceToHost, ctx->stream));
     HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const int32_t n = *reinterpret_cast<int32_t*>(hr);
     const int32_t* h_q = reinterpret_cast<int32_t*>(hr + 16);
@@ -749,17 +848,24 @@ HM_API int hm_frame_match(hm_context* ctx, int train_slot, int query_slot, unsig
     int32_t* d_pq = d_d + nq;          // 16 + 12 nq bytes: 8-byte aligned when nq is even; padded below otherwise
     if (nq & 1) ++d_pq;
     int32_t* d_pt = d_pq + 2 * nq;
-    rc = hm_match_fused(Q.d, nq, HM_DESC_BYTES, 0, T.d, nt, HM_DESC_BYTES, 0, 1, flags, ratio_lut_host, dist_threshold, d_q,
-                        d_t, d_d, d_count, nullptr, variant, dw, wsb, ctx->stream);
+    const size_t out_bytes = want_pts ? (size_t)(reinterpret_cast<uint8_t*>(d_pt + 2 * nq) - dr) : 16 + (size_t)nq * 12;
+    GraphKey key;
+    fill_key(&key, 1, nq, nt, flags, variant, want_pts ? 1 : 0, ratio_lut_host, dist_threshold);
+    key.ptr[0] = ctx->d_buf; key.ptr[1] = ctx->h_buf; key.ptr[2] = Q.d; key.ptr[3] = T.d;
+    rc = run_cached_graph(ctx, key, [&]() -> int {
+        int r = hm_match_fused(Q.d, nq, HM_DESC_BYTES, 0, T.d, nt, HM_DESC_BYTES, 0, 1, flags, ratio_lut_host,
+                               dist_threshold, d_q, d_t, d_d, d_count, nullptr, variant, dw, wsb, ctx->stream);
+        if (r != HM_OK) return r;
+        if (want_pts) {
+            r = hm_gather_points(d_q, d_t, d_count, nq, 1, reinterpret_cast<const int32_t*>(Q.d + slot_points_offset(nq)),
+                                 nq, reinterpret_cast<const int32_t*>(T.d + slot_points_offset(nt)), nt, d_pq, d_pt,
+                                 ctx->stream);
+            if (r != HM_OK) return r;
+        }
+        HM_CUDA_CHECK(cudaMemcpyAsync(hr, dr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        return HM_OK;
+    });
     if (rc != HM_OK) return rc;
-    size_t out_bytes = 16 + (size_t)nq * 12;
-    if (want_pts) {
-        rc = hm_gather_points(d_q, d_t, d_count, nq, 1, reinterpret_cast<const int32_t*>(Q.d + slot_points_offset(nq)), nq,
-                              reinterpret_cast<const int32_t*>(T.d + slot_points_offset(nt)), nt, d_pq, d_pt, ctx->stream);
-        if (rc != HM_OK) return rc;
-        out_bytes = (size_t)(reinterpret_cast<uint8_t*>(d_pt + 2 * nq) - dr);
-    }
-    HM_CUDA_CHECK(cudaMemcpyAsync(hr, dr, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     const int32_t n = *reinterpret_cast<int32_t*>(hr);
     const int32_t* h_q = reinterpret_cast<int32_t*>(hr + 16);

@@ -305,3 +305,32 @@ def test_batched_split_launch(variant):
     keys = nat.knn2_keys_batched(dev(q), dev(t), variant=variant).cpu().numpy().view(np.uint64)
     for i in range(b):
         assert np.array_equal(keys[i], co.knn2_keys(q[i], t[i])), i
+
+
+def test_host_calls_replay_cuda_graphs_with_fresh_data():
+    """The host-buffer entry points capture a CUDA graph of their stream sequence the second time a shape is
+    seen and replay it afterwards: every replay must see that call's data, flags and thresholds."""
+    rng = np.random.default_rng(99)
+    ctx = nat.HostContext()
+    for nq, nt in ((200, 200), (333, 1500)):
+        for it in range(5):                                   # direct, capture, replay, replay, replay
+            q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+            t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+            q[: nq // 2] = t[rng.choice(nt, nq // 2, replace=False)] ^ rng.integers(0, 2, (nq // 2, 32), dtype=np.uint8)
+            for kwargs in ({}, {"ratio": 0.75, "cross_check": True}, {"ratio": 0.8}, {"dist_threshold": 30.0}):
+                gq, gt, gd = ctx.match(q, t, **kwargs)
+                if "dist_threshold" in kwargs:
+                    eq, et, ed = ho.reference_match(t, q, 30.0)
+                else:
+                    eq, et, ed = co.pipeline(q, t, kwargs.get("ratio"), kwargs.get("cross_check", False))
+                assert np.array_equal(gq, eq) and np.array_equal(gt, et) and np.array_equal(gd, ed), (nq, nt, it, kwargs)
+            # resident frames: same slots, new contents every iteration
+            pos_q = rng.integers(0, 700, (nq, 2)).astype(np.int32)
+            pos_t = rng.integers(0, 700, (nt, 2)).astype(np.int32)
+            ctx.frame_put(0, t, pos_t)
+            ctx.frame_put(1, q, pos_q)
+            gq, gt, gd, pq, pt = ctx.frame_match(0, 1, nq, ratio=0.75, cross_check=True, want_points=True)
+            eq, et, ed = co.pipeline(q, t, 0.75, True)
+            assert np.array_equal(gq, eq) and np.array_equal(gt, et) and np.array_equal(gd, ed)
+            assert np.array_equal(pq, pos_q[eq]) and np.array_equal(pt, pos_t[et])
+    ctx.close()
