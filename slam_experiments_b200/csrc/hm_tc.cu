@@ -554,7 +554,14 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             if (warp == 9 && lane == 0) trace_mark(P, i, 5);
             ptx::tc_fence_after();
             if constexpr (kFloor) {
-                if (i < 8 || (i & 3) == 0) {                 // every tile at first, then every fourth
+#ifndef HM_FLOOR_CADENCE
+#define HM_FLOOR_CADENCE 31
+#endif
+                // every tile at first, then every 16th, later every 32nd: the refresh itself (an atomicMax when the
+                // thread's second best improved, one L2 load) costs more than it saves when done too often -- cycles
+                // per tile on a 217-tile CTA: every 2nd 1169, 4th 1077, 8th 1033, 16th 1027, 32nd 1044; on the
+                // 1730-tile CTAs of C4: 16th 724, 32nd 714 (without the thresholds: 784)
+                if (i < 8 || (i & (i < 512 ? 15 : HM_FLOOR_CADENCE)) == 0) {
                     // the code loaded at the previous refresh is consumed now, so the load's latency is hidden
                     s.f = C::max2(s.f, C::floor_from(floor_code));
                     if (row < P.nq) {
@@ -681,7 +688,19 @@ int floor_max_tiles()
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("HM_FLOOR_MAX_TILES");
-        v = e ? atoi(e) : 1300;   // f4, 2000 queries: 217 tiles per CTA +30 %, 433 +17 %, 865 +7 %, 1730 -3 %
+        v = e ? atoi(e) : 0x7fffffff;
+    }
+    return v;
+}
+
+// unsplit launches use the floor kernels (thresholds shared by the two column-half warps of a row) from this
+// many tiles per CTA on (HM_FLOOR_MIN_TILES_UNSPLIT overrides; 0x7fffffff = never)
+int floor_min_tiles_unsplit()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HM_FLOOR_MIN_TILES_UNSPLIT");
+        v = e ? atoi(e) : 0x7fffffff;
     }
     return v;
 }
@@ -845,16 +864,23 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
         P.out = partials;                  // even with one split: the exchange runs in the last-CTA path
         P.out_split_stride = rows * 2;
     }
+    // shared row thresholds: the CTAs (and, with kColSplit == 2, the two column-half warps) of a query row
+    bool zero_block = false;
+    const bool floor_eligible = !top1 && pl.tiles_per_split <= floor_max_tiles() &&
+                                (pl.splits > 1 || (C::kColSplit > 1 && pl.ntiles >= floor_min_tiles_unsplit()));
+    if (floor_eligible) {
+        P.row_floor = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(counters) + counters_bytes(pl.qblocks * batch));
+        zero_block = true;
+    }
     if ((pl.splits > 1 || fused_exchange) && !keep_partials) {   // merge in-kernel: last CTA per query block writes `out`
         P.counters = counters;
         P.final_out = out;
-        if (pl.splits > 1 && pl.tiles_per_split <= floor_max_tiles() && !top1)
-            P.row_floor = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(counters) + counters_bytes(pl.qblocks * batch));
-        HM_CUDA_CHECK(cudaMemsetAsync(counters, 0, cbytes, stream));
+        zero_block = true;
     } else if (!(pl.splits > 1 || keep_partials)) {
         P.out = out;
         P.out_split_stride = 0;
     }
+    if (zero_block) HM_CUDA_CHECK(cudaMemsetAsync(counters, 0, cbytes, stream));
     if (pl.qblocks > 0x7FFFFFFFll || pl.splits > 65535 || batch > 65535) {
         set_error("grid too large");
         return HM_ERR_UNSUPPORTED;
