@@ -341,7 +341,8 @@ def run_b200(args):
         kind = "kind::i8" if variant_used == "i8" else "kind::mxf4"
         peak = mult * peaks["bf16_tflops_sustained"]
         # shards whose CTAs see <= 1300 tiles run the *_floor twin of the kernel (shared row thresholds)
-        roofline = {"bound": "tensor", "kernel": f"hm_{variant_used}_knn2_kernel", "achieved": achieved, "peak": peak,
+        launch = nat.describe_launch(NQ, nt_local, 1, variant_used)
+        roofline = {"bound": "tensor", "kernel": launch.split()[0], "launch": launch, "achieved": achieved, "peak": peak,
                     "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
                     "note": f"+/-1 multiply-add ops (512/pair); peak = {mult:g} x bf16_tflops_sustained of {peak_src} "
                             f"({kind} issues at {mult:g}x the bf16 rate)",

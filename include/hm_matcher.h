@@ -86,6 +86,9 @@ HM_API const char* hm_last_error(void);
 HM_API int hm_device_sm_count(void);
 /* the variant HM_VARIANT_AUTO resolves to for this shape */
 HM_API int hm_select_variant(int64_t nq, int64_t nt, int batch);
+/* which kernel (and grid) hm_knn2* launches for this shape, as text: "hm_f4_knn2_floor_kernel grid=(8,37,1)
+ * cluster=2 tiles_per_cta=1730"; for bench lines and profiles, not part of the data path */
+HM_API int hm_describe_launch(int64_t nq, int64_t nt, int batch, int variant, char* buf, size_t buf_bytes);
 /* scratch bytes hm_knn2* / hm_match_fused* need for this shape (variant may be AUTO) */
 HM_API size_t hm_workspace_bytes(int64_t nq, int64_t nt, int batch, int variant);
 

@@ -31,6 +31,7 @@ PREPARED_ROW_BYTES = {VARIANT_I8: 256, VARIANT_F4: 128}
 # every symbol include/hm_matcher.h declares (tests check the library exports all of them)
 EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
+    "hm_describe_launch",
     "hm_knn2", "hm_knn2_batched", "hm_default_tensor_variant", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials", "hm_knn2_prepared_exchange",
     "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused", "hm_gather_points", "hm_rasterize_mask",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host", "hm_frame_put", "hm_frame_match",
@@ -55,6 +56,8 @@ def _declare(L):
     L.hm_profile_events.argtypes = [vp, vp]
     L.hm_select_variant.restype = ci
     L.hm_select_variant.argtypes = [i64, i64, ci]
+    L.hm_describe_launch.restype = ci
+    L.hm_describe_launch.argtypes = [i64, i64, ci, ci, c.c_char_p, sz]
     L.hm_workspace_bytes.restype = sz
     L.hm_workspace_bytes.argtypes = [i64, i64, ci, ci]
     L.hm_knn2.restype = ci
@@ -443,6 +446,13 @@ def profile_events(start: Optional[torch.cuda.Event], stop: Optional[torch.cuda.
         if not e.cuda_event:
             e.record()
     lib().hm_profile_events(start.cuda_event, stop.cuda_event)
+
+
+def describe_launch(nq: int, nt: int, batch: int = 1, variant="auto") -> str:
+    """``hm_describe_launch``: kernel name and grid the k-NN call would use for this shape."""
+    buf = ctypes.create_string_buffer(256)
+    check(lib().hm_describe_launch(nq, nt, batch, variant_id(variant), buf, 256), "hm_describe_launch")
+    return buf.value.decode()
 
 
 def sm_count() -> int:

@@ -205,6 +205,26 @@ HM_API int hm_device_sm_count(void)
 
 HM_API int hm_select_variant(int64_t nq, int64_t nt, int batch) { return select_variant(nq, nt, batch); }
 
+HM_API int hm_describe_launch(int64_t nq, int64_t nt, int batch, int variant, char* buf, size_t buf_bytes)
+{
+    if (!buf || buf_bytes == 0 || nq <= 0 || nt <= 0 || batch <= 0) {
+        set_error("hm_describe_launch: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    DeviceInfo di;
+    int sm = 148;   // B200; the real count when a device is visible
+    if (device_info(&di) == HM_OK) sm = di.sm_count;
+    const int v = resolve_variant(variant, nq, nt, batch);
+    if (v == HM_VARIANT_POPC) {
+        KnnProblem p{};
+        p.nq = nq; p.nt = nt; p.batch = batch;
+        snprintf(buf, buf_bytes, "hm_popc_knn2_kernel splits=%d", popc_splits(p, sm));
+    } else {
+        describe_tc_launch(nq, nt, batch, sm, v, false, buf, buf_bytes);
+    }
+    return HM_OK;
+}
+
 HM_API size_t hm_workspace_bytes(int64_t nq, int64_t nt, int batch, int variant)
 {
     DeviceInfo di;

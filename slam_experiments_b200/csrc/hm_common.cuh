@@ -226,6 +226,7 @@ int launch_filter(const unsigned long long* fwd, long long nq, const unsigned lo
                   int batch, unsigned flags, const RatioLut& lut, int thr_ceil, int* out_q, int* out_t,
                   int* out_d, int* out_count, cudaStream_t stream);
 
+void describe_tc_launch(long long nq, long long nt, int batch, int sm_count, int variant, bool top1, char* buf, size_t n);
 int launch_gather_points(const int* q_idx, const int* t_idx, const int* count, long long stride, int batch,
                          const int* query_pts, long long nq, const int* train_pts, long long nt, int* out_query,
                          int* out_train, cudaStream_t stream);

@@ -998,6 +998,22 @@ int launch_tc_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
                                          out_partials, out_groups, exchange);
 }
 
+// "kernel grid=(x,y,z) cluster=c" of the launch the given shape would get (introspection for bench / docs)
+template <class C>
+static void describe_of(long long nq, long long nt, int batch, int sm_count, bool top1, char* buf, size_t n)
+{
+    const TcPlan pl = plan_tc<C>(nq, nt, batch, sm_count);
+    const bool floor = !top1 && pl.splits > 1 && pl.tiles_per_split <= floor_max_tiles();
+    snprintf(buf, n, "hm_%s_knn%s%s_kernel grid=(%lld,%d,%d) cluster=%d tiles_per_cta=%d", C::kScales ? "f4" : "i8",
+             top1 ? "1" : "2", floor ? "_floor" : "", pl.qblocks, pl.splits, batch, pl.cluster, pl.tiles_per_split);
+}
+
+void describe_tc_launch(long long nq, long long nt, int batch, int sm_count, int variant, bool top1, char* buf, size_t n)
+{
+    if (variant == HM_VARIANT_F4) describe_of<CoreF4>(nq, nt, batch, sm_count, top1, buf, n);
+    else                          describe_of<CoreI8>(nq, nt, batch, sm_count, top1, buf, n);
+}
+
 int launch_tc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count, int variant,
                    cudaStream_t stream)
 {

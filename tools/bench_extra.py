@@ -202,7 +202,8 @@ def run(args):
         ach = kpairs * I8_OPS_PER_PAIR / (kms * 1e-3) / 1e12
         mult = 2.0 if variant == "i8" else 4.0
         peak = mult * peaks["bf16_tflops"]
-        roof = {"bound": "tensor", "kernel": f"hm_{variant}_knn2_kernel", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+        launch = nat.describe_launch(nq_k, nt_k, 1 if wl in ("c3", "c1") else nb, variant)
+        roof = {"bound": "tensor", "kernel": launch.split()[0], "launch": launch, "achieved": ach, "peak": peak, "unit": "TFLOP/s",
                 "frac": ach / peak, "traffic": None, "kernel_ms": kms,
                 "note": f"+/-1 multiply-add ops (512/pair); peak = {mult:g} x bf16_tflops (burst: kernel timed alone) of {peak_src}"}
     else:
