@@ -68,3 +68,15 @@ def test_compute_fails_loudly_without_gpu(lib):
     h = ctypes.c_void_p()
     assert lib.hm_context_create(ctypes.byref(h)) == -5
     assert lib.hm_device_sm_count() == -5
+
+
+def test_describe_launch_without_a_device(lib):
+    """Launch planning is host arithmetic: it answers without a GPU (148 SMs assumed)."""
+    d = nat.describe_launch
+    assert d(200, 200).startswith("hm_popc_knn2_kernel")
+    c4 = d(2000, 8192000, 1, "f4")
+    assert c4.startswith("hm_f4_knn2_floor_kernel grid=(8,") and "cluster=2" in c4      # 8 query blocks, train split
+    assert d(2000, 8192000, 1, "i8").startswith("hm_i8_knn2_floor_kernel")
+    assert d(2000, 2000, 99).startswith(("hm_f4_knn2_kernel grid=(8,1,99)", "hm_i8_knn2_kernel grid=(8,1,99)"))
+    with pytest.raises(nat.NativeError):
+        d(0, 5)
