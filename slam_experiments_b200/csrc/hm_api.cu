@@ -74,7 +74,7 @@ namespace {
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
 // Static per-shape table ("variant selection"): the tensor-core variant pays an
-// operand-expansion pre-pass (two more launches, ~3 us each); kernel-only times (profiles/r02c_probe_shapes.txt):
+// operand-expansion pre-pass (two more launches, ~3 us each); kernel-only times (profiles/r01p_probe_shapes.txt):
 // 2000 x 2000 POPC 22 us vs tensor 15 + 6 us, 4096 x 4096 52 us vs 22 + 6 us -- crossover near 8e6 pairs.
 // The tensor-core core AUTO resolves to.  HM_TENSOR_CORE=i8|f4 overrides it for experiments.
 int default_tensor_variant()
