@@ -14,10 +14,12 @@
 // One CTA owns 256 query rows (two 128-row A blocks, resident in shared memory) and streams 128-row
 // train tiles (B operand) through a ring of bulk-async-copy stages.  Per (tile, query block) a single
 // elected thread issues the MMAs (M=128, N=128) into one of the 128-column TMEM accumulator units;
-// eight epilogue warps (one per 32 query rows) read finished units with tcgen05.ld (thread = query
-// row, registers = train columns) and keep the running top-2 in registers, so the distance tile never
-// leaves the SM.  kind::i8 uses four units (2 query blocks x 2 buffers = all 512 columns); kind::mxf4
-// rotates three units and keeps its scale factors in the last 128 columns.
+// epilogue warps (kind::i8: eight, one per 32 query rows; kind::mxf4: sixteen, two column halves per
+// lane quarter) read finished units with tcgen05.ld (thread = query row, registers = train columns) and
+// keep the running top-2 in registers, so the distance tile never leaves the SM.  kind::i8 uses four
+// units (2 query blocks x 2 buffers = all 512 columns); kind::mxf4 rotates three units and keeps its
+// scale factors in the last 128 columns.  Three kernels per core: top-2, top-2 with row thresholds shared
+// by all CTAs of a query row (split launches), top-1 (passes whose second neighbour nobody reads).
 //
 // Why this shape (ncu, profiles/r01a_* .. r01g_*): the +/-1 operands are 8x (4x) larger than the
 // packed bits, so with 128 query rows per CTA each tile needs 64 B/clk/SM of L2->SM traffic and two
