@@ -7,6 +7,7 @@ calls raise ``NativeError``.
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes
 import os
 import threading
@@ -142,6 +143,17 @@ def require_cuda(device=None) -> torch.device:
     return dev
 
 
+_NULL_CONTEXT = contextlib.nullcontext()
+
+
+def on_device(dev: torch.device):
+    """Context manager that makes ``dev`` current -- a shared no-op object when it already is (torch's own
+    context manager costs ~10 us per use, which is visible on the small-problem and end-to-end paths)."""
+    if torch.cuda.current_device() == dev.index:
+        return _NULL_CONTEXT
+    return torch.cuda.device(dev)
+
+
 def variant_id(variant) -> int:
     try:
         return VARIANTS[variant]
@@ -194,7 +206,7 @@ def knn2_keys(query: torch.Tensor, train: torch.Tensor, train_base: int = 0, var
         out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
     v = variant_id(variant)
     L = lib()
-    with torch.cuda.device(dev):
+    with on_device(dev):
         wsb = L.hm_workspace_bytes(nq, nt, 1, v)
         ws = workspace(wsb, dev)
         check(L.hm_knn2(query.data_ptr(), nq, query.stride(0) if nq else DESC_BYTES,
@@ -216,7 +228,7 @@ def knn2_keys_batched(query: torch.Tensor, train: torch.Tensor, variant="auto",
         out = torch.empty((b, nq, 2), dtype=torch.int64, device=dev)
     v = variant_id(variant)
     L = lib()
-    with torch.cuda.device(dev):
+    with on_device(dev):
         wsb = L.hm_workspace_bytes(nq, nt, b, v)
         ws = workspace(wsb, dev)
         check(L.hm_knn2_batched(query.data_ptr(), nq, query.stride(1) if nq else DESC_BYTES, query.stride(0),
@@ -242,7 +254,7 @@ def prepare(bits: torch.Tensor, out: Optional[torch.Tensor] = None, variant="aut
         out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     elif out.numel() < nbytes:
         raise ValueError("prepared buffer too small")
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib().hm_prepare(bits.data_ptr(), n, bits.stride(0) if n else DESC_BYTES, out.data_ptr(), v,
                                _stream_ptr(dev)), "hm_prepare")
     return out
@@ -255,7 +267,7 @@ def knn2_keys_prepared(query_prepared: torch.Tensor, nq: int, train_prepared: to
         out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
     v = tensor_variant(variant)
     L = lib()
-    with torch.cuda.device(dev):
+    with on_device(dev):
         wsb = L.hm_prepared_workspace_bytes(nq, nt, v)
         ws = workspace(wsb, dev)
         check(L.hm_knn2_prepared(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
@@ -271,7 +283,7 @@ def merge_top2(keys: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.
     g, rows = keys.shape[0], keys.shape[1]
     if out is None:
         out = torch.empty((rows, 2), dtype=torch.int64, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib().hm_merge_top2(keys.data_ptr(), g, rows, out.data_ptr(), _stream_ptr(dev)), "hm_merge_top2")
     return out
 
@@ -294,7 +306,7 @@ def exchange_merge(local_keys, world: int, rank: int, peer_ptrs, max_rows: int, 
     if out is None:
         out = torch.empty((rows, 2), dtype=torch.int64, device=dev)
     arr = peer_ptrs if isinstance(peer_ptrs, ctypes.Array) else (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib().hm_exchange_merge(ptr, groups, rows, world, rank, arr, max_rows, epoch, out.data_ptr(),
                                       _stream_ptr(dev)), "hm_exchange_merge")
     return out
@@ -310,7 +322,7 @@ def knn2_prepared_exchange(query_prepared: torch.Tensor, nq: int, train_prepared
     arr = peer_ptrs if isinstance(peer_ptrs, ctypes.Array) else (ctypes.c_void_p * world)(*[int(p) for p in peer_ptrs])
     v = tensor_variant(variant)
     L = lib()
-    with torch.cuda.device(dev):
+    with on_device(dev):
         wsb = L.hm_prepared_workspace_bytes(nq, nt, v)
         ws = workspace(wsb, dev)
         check(L.hm_knn2_prepared_exchange(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
@@ -327,7 +339,7 @@ def knn2_partials_prepared(query_prepared: torch.Tensor, nq: int, train_prepared
     L = lib()
     parts, groups = ctypes.c_void_p(), ctypes.c_int(0)
     v = tensor_variant(variant)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         wsb = L.hm_prepared_workspace_bytes(nq, nt, v)
         ws = workspace(wsb, dev)
         check(L.hm_knn2_prepared_partials(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
@@ -387,7 +399,7 @@ def match_fused(query: torch.Tensor, train: torch.Tensor, ratio: Optional[float]
     keys = torch.empty((b, nq, 2), dtype=torch.int64, device=dev) if want_keys else None
     v = variant_id(variant)
     L = lib()
-    with torch.cuda.device(dev):
+    with on_device(dev):
         wsb = L.hm_workspace_bytes(nq, nt, b, v)
         ws = workspace(wsb, dev)
         check(L.hm_match_fused(query.data_ptr(), nq, query.stride(1) if nq else DESC_BYTES, query.stride(0),
@@ -413,7 +425,7 @@ def gather_points(q_idx: torch.Tensor, t_idx: torch.Tensor, count: torch.Tensor,
     dev = q_idx.device
     oq = torch.empty((b, stride, 2), dtype=torch.int32, device=dev)
     ot = torch.empty((b, stride, 2), dtype=torch.int32, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib().hm_gather_points(q_idx.data_ptr(), t_idx.data_ptr(), count.data_ptr(), stride, b,
                                      query_pts.data_ptr(), query_pts.shape[1], train_pts.data_ptr(), train_pts.shape[1],
                                      oq.data_ptr(), ot.data_ptr(), _stream_ptr(dev)), "hm_gather_points")
@@ -430,7 +442,7 @@ def rasterize_mask(points: torch.Tensor, shape, radius: int, inner: bool = True,
     dev = points.device
     if out is None:
         out = torch.empty((h, w), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    with on_device(dev):
         check(lib().hm_rasterize_mask(points.data_ptr(), points.shape[0], int(radius), 1 if inner else 0,
                                       out.data_ptr(), h, w, out.stride(0) if h else w, _stream_ptr(dev)), "hm_rasterize_mask")
     return out

@@ -128,7 +128,7 @@ class FrameDescriptorStore:
 
     def _put_slot(self, frame_id, a: np.ndarray, positions) -> None:
         if self._ctx is None:
-            with torch.cuda.device(self.device):
+            with nat.on_device(self.device):
                 self._ctx = nat.HostContext()
         if frame_id in self._slots:
             slot = self._slots.pop(frame_id)[0]
@@ -145,7 +145,7 @@ class FrameDescriptorStore:
             if pos.ndim != 2 or pos.shape[1] != 2 or pos.shape[0] != a.shape[0]:
                 raise MatcherError(f"positions: expected [{a.shape[0]}, 2], got {pos.shape}")
             pos = pos.astype(np.int32, copy=False)
-        with torch.cuda.device(self.device):
+        with nat.on_device(self.device):
             self._ctx.frame_put(slot, a, pos)
         self._slots[frame_id] = (slot, a.shape[0], pos is not None)
         if frame_id in self._frames:
@@ -175,7 +175,7 @@ class FrameDescriptorStore:
                 p = np.empty((0, 2), np.int32)
             if p.ndim != 2 or p.shape[1] != 2 or p.shape[0] != t.shape[0]:
                 raise MatcherError(f"positions: expected [{t.shape[0]}, 2], got {p.shape}")
-            with torch.cuda.device(self.device):
+            with nat.on_device(self.device):
                 self._points[frame_id] = torch.from_numpy(np.ascontiguousarray(p.astype(np.int32))).to(self.device)
         while len(self._frames) > self.capacity:
             old, _ = self._frames.popitem(last=False)
@@ -189,7 +189,7 @@ class FrameDescriptorStore:
         (ts, nt, tp), (qs, nq, qp) = self._slots[last_id], self._slots[current_id]
         if want_points and not (tp and qp):
             raise MatcherError("matched_points needs both frames stored with positions")
-        with torch.cuda.device(self.device):
+        with nat.on_device(self.device):
             return self._ctx.frame_match(ts, qs, nq, ratio=self.ratio, cross_check=self.cross_check,
                                          dist_threshold=dist_threshold if dist_threshold else None, variant=self.variant,
                                          want_indices=want_indices, want_points=want_points)

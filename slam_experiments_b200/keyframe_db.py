@@ -64,7 +64,7 @@ class NativeOps:
         """Host -> device through a reused pinned buffer (queries); big one-off uploads go direct."""
         a = np.asarray(a)
         if a.nbytes <= (8 << 20):
-            with torch.cuda.device(self.device):
+            with nat.on_device(self.device):
                 return self._staging.to_device("q", a, self.device)
         return torch.from_numpy(np.ascontiguousarray(a, dtype=np.uint8)).to(self.device)
 
@@ -88,7 +88,7 @@ class NativeOps:
         if n == 0:
             return shard
         nt, new_nt = shard["nt"], shard["nt"] + n
-        with torch.cuda.device(self.device):
+        with nat.on_device(self.device):
             buf = shard.get("buf")
             if buf is None or buf.shape[0] < new_nt:
                 cap = max(2 * new_nt, 4096)
@@ -143,7 +143,7 @@ class NativeOps:
             import torch.distributed as dist
             import torch.distributed._symmetric_memory as symm
             nbytes = nat.exchange_bytes(max_rows, world)
-            with torch.cuda.device(self.device):
+            with nat.on_device(self.device):
                 buf = symm.empty(nbytes, dtype=torch.uint8, device=self.device)
                 buf.zero_()
                 torch.cuda.synchronize(self.device)
@@ -184,7 +184,7 @@ class NativeOps:
         return self.merge(self.all_gather(local, group))
 
     def to_host(self, keys: torch.Tensor) -> np.ndarray:
-        with torch.cuda.device(self.device):
+        with nat.on_device(self.device):
             return self._staging.to_host("keys", keys)
 
 
