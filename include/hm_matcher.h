@@ -212,7 +212,8 @@ HM_API int hm_rasterize_mask(const int32_t* points, int64_t n, int radius, int i
                              uint8_t* mask, int h, int w, int64_t row_stride, void* stream);
 
 /* ---- host-buffer convenience (what a non-torch caller binds) --------------------------- */
-typedef struct hm_context hm_context; /* owns a stream, device scratch and pinned staging */
+typedef struct hm_context hm_context; /* owns a stream, device scratch, pinned staging, frame slots and a small
+                                         cache of CUDA graphs; one context per calling thread (not thread-safe) */
 HM_API int hm_context_create(hm_context** out_ctx);
 HM_API void hm_context_destroy(hm_context* ctx);
 /* numpy-in / numpy-out twin of hm_knn2: H2D, kernels, D2H, synchronises before returning */

@@ -659,7 +659,7 @@ static int run_cached_graph(hm_context* ctx, const GraphKey& key, F&& enqueue)
             if (graph) cudaGraphDestroy(graph);
             e->exec = nullptr;
             e->uses = -1;
-            return rc != HM_OK ? rc : enqueue();     // nothing ran during the failed capture
+            return enqueue();                        // nothing ran during the failed capture: run it directly
         }
         cudaGraphDestroy(graph);
     }
