@@ -6,7 +6,7 @@ import torch
 
 import slam_experiments_b200 as sx
 from conftest import load_golden, golden_files
-from oracle import hamming_oracle as ho
+from oracle import glue_oracle as go, hamming_oracle as ho
 
 cv2 = pytest.importorskip("cv2")
 
@@ -130,8 +130,7 @@ def test_matched_points_gathered_on_device():
             store.put("cur", cur.get_descriptors(), pos_cur)
             sp, qp = store.matched_points("last", "cur", dist_thr)
             matches = store.match("last", "cur", dist_thr)                       # same matches as DMatch objects
-            ref_s = np.array([last.features[m.trainIdx].position for m in matches]).reshape(-1, 2)
-            ref_q = np.array([cur.features[m.queryIdx].position for m in matches]).reshape(-1, 2)
+            ref_s, ref_q = go.matched_point_lists(matches, pos_last, pos_cur)          # utils.py:13-19
             assert sp.dtype == np.int32 and np.array_equal(sp, ref_s) and np.array_equal(qp, ref_q)
         store.put("none", np.array([]), np.empty((0, 2)))
         sp, qp = store.matched_points("last", "none")
@@ -157,12 +156,7 @@ def test_detection_mask_equals_cv2_rectangles():
     reference, rasterised on the device -- identical masks, borders and out-of-image points included."""
     rng = np.random.default_rng(11)
 
-    def reference(shape, pos, radius, inner):              # utils.py:66-74 on Feature.position arrays
-        mask = np.full(shape, fill_value=0 if inner else 255, dtype=np.uint8)
-        shift = np.array([radius, radius])
-        for pt in pos:
-            mask = cv2.rectangle(mask, pt - shift, pt + shift, 255 if inner else 0, cv2.FILLED)
-        return mask
+    reference = go.detection_mask                          # utils.py:66-74 on Feature.position arrays
 
     for shape, n, radius in (((480, 752), 2000, 10), ((480, 640), 200, 10), ((33, 47), 40, 3), ((5, 9), 6, 0), ((64, 64), 0, 4)):
         pos = np.stack([rng.integers(-15, shape[1] + 15, n), rng.integers(-15, shape[0] + 15, n)], 1).astype(np.int32)

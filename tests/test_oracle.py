@@ -137,3 +137,21 @@ def test_oracles_vs_cv2_live():
         mq, mt, md, _ = cv2_ref.dmatches_to_arrays(m)
         oq, ot, od = ho.reference_match(t, q, 40.0)
         assert np.array_equal(mq, oq) and np.array_equal(mt, ot) and np.array_equal(md, od)
+
+
+def test_glue_oracle_mask_numpy_equals_cv2_rectangles():
+    """The detection-mask restatement (utils.py:58-74): its numpy branch equals its cv2.rectangle branch,
+    including squares that leave the image."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import glue_oracle as go
+    rng = np.random.default_rng(4)
+    for shape, n, r in (((48, 64), 30, 5), ((7, 9), 8, 0), ((20, 20), 12, 30)):
+        pos = np.stack([rng.integers(-10, shape[1] + 10, n), rng.integers(-10, shape[0] + 10, n)], 1).astype(np.int32)
+        for inner in (True, False):
+            with_cv2 = go.detection_mask(shape, pos, r, inner)
+            saved, go.cv2 = go.cv2, None
+            try:
+                plain = go.detection_mask(shape, pos, r, inner)
+            finally:
+                go.cv2 = saved
+            assert np.array_equal(with_cv2, plain)
