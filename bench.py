@@ -157,9 +157,48 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi"}
 
 
-def make_c4(n_keyframes=N_KEYFRAMES, rows=KF_ROWS, nq=NQ):
-    from slam_experiments_b200 import synth
-    return synth.keyframe_database(n_keyframes, rows, nq, seed=4096)
+def _load_synth():
+    """slam_experiments_b200/synth.py loaded BY PATH (it only needs numpy): the reference arm must not import the
+    product package, whose __init__ loads the native libraries."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_hm_synth", os.path.join(ROOT, "slam_experiments_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def make_c4(n_keyframes=N_KEYFRAMES, rows=KF_ROWS, nq=NQ, dist="M"):
+    """C4 inputs.  "M" (default, SURVEY.md 8d): matchable queries over a uniform database; "U": uniform queries;
+    "monotone": the adversarial input of SURVEY.md 7 -- near-identical queries and the database sorted by
+    DEcreasing distance to them, so every CTA streams monotonically improving, massively tied distances."""
+    synth = _load_synth()
+    query, train = synth.keyframe_database(n_keyframes, rows, nq, seed=4096)
+    if dist == "U":
+        query = synth.uniform(nq, 4097)
+    elif dist == "monotone":
+        rng = np.random.default_rng(4098)
+        base = rng.integers(0, 256, 32, dtype=np.uint8)
+        d = np.bitwise_count(train ^ base).sum(axis=1, dtype=np.int32)
+        train = np.ascontiguousarray(train[np.argsort(-d, kind="stable")])
+        query = np.repeat(base[None, :], nq, axis=0)
+        flips = rng.integers(0, 256, (nq, 3))                    # three random bit flips per query row
+        for j in range(3):
+            query[np.arange(nq), flips[:, j] >> 3] ^= (1 << (flips[:, j] & 7)).astype(np.uint8)
+    return query, train
+
+
+def mma_issue_peak(variant):
+    """TOP/s of a pure tcgen05.mma issue loop on this chip, measured by tools/microbench*.cu (committed JSON)."""
+    key = "mma_mxf4_n128_chip_tops" if variant == "f4" else "mma_i8_n128_chip_tops"
+    for name in ("r01h_microbench_fp4_b200.json", "r01_microbench_b200.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                d = json.load(f)
+            if key in d:
+                return float(d[key]), f"profiles/{name}:{key}"
+        except Exception:
+            pass
+    return (8838.2 if variant == "f4" else 4557.8), "fallback constant (microbench JSON missing)"
 
 
 # =====================================================================================================
@@ -175,13 +214,20 @@ def cv2_collection_step(query, keyframes):
 
 def calibrate_sample(query, train, target_s: float, rows=KF_ROWS, max_kf=N_KEYFRAMES):
     """Number of keyframes whose cv2 collection query takes about `target_s` seconds."""
-    probe = 8
-    kfs = [train[i * rows:(i + 1) * rows] for i in range(probe)]
-    cv2_collection_step(query, kfs)
-    t0 = time.perf_counter()
-    cv2_collection_step(query, kfs)
-    dt = max(time.perf_counter() - t0, 1e-4)
-    n = int(probe * target_s / dt)
+    n = 8
+    for _ in range(3):                       # refine: tiny probes are dominated by thread start-up
+        kfs = [train[i * rows:(i + 1) * rows] for i in range(n)]
+        cv2_collection_step(query, kfs)
+        t0 = time.perf_counter()
+        cv2_collection_step(query, kfs)
+        dt = max(time.perf_counter() - t0, 1e-4)
+        est = int(n * target_s / dt)
+        if dt >= 0.25 * target_s or n >= max_kf:
+            n = est
+            break
+        n = max(n + 1, min(max_kf, est, n * 16))
+    else:
+        n = est
     return max(2, min(max_kf, n))
 
 
@@ -190,10 +236,10 @@ def run_reference(args):
     if rank != 0:
         return 0
     import cv2
-    from oracle import cv2_ref  # noqa: F401  (the reference class restated over cv2; checker-side code)
     query, train = make_c4()
-    # bounded sample: the whole (warmup + steps) run stays near two minutes whatever K is
-    per_step = max(0.05, min(3.0, 120.0 / max(1, args.steps + args.warmup)))
+    # bounded sample: the whole (warmup + steps) run stays near two to three minutes whatever K is; when the full
+    # database fits that budget (few steps) the step IS the full config
+    per_step = max(0.05, min(8.0, 150.0 / max(1, args.steps + args.warmup)))
     n_kf = calibrate_sample(query, train, per_step)
     kfs = [train[i * KF_ROWS:(i + 1) * KF_ROWS] for i in range(n_kf)]
     for _ in range(args.warmup):
@@ -209,7 +255,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": c4_config(args.gpus),
+        "config": dict(c4_config(args.gpus), same_config=bool(n_kf == N_KEYFRAMES)),
+        "native_so_loaded": [m for m in sys.modules if m.startswith("slam_experiments_b200")],   # must stay empty
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cv2.getNumThreads(), "kind": "reference",
                          "sample": sample, "engine": f"cv2.BFMatcher {cv2.__version__}",
                          "host_cpus": os.cpu_count()},
@@ -229,6 +276,81 @@ def c4_config(n_gpus):
 # =====================================================================================================
 # B200 arm
 # =====================================================================================================
+def verify_all_rows(db, q_dev, query, train, rank, world, dist, dev):
+    """Correctness of what is timed, outside the timed region: EVERY row on EVERY rank.
+
+    The keys a rank holds are compared bit for bit with rank 0's (broadcast), and the oracle's work is split over the
+    ranks (rank r checks rows r::world with its share of the host threads), so all rows are checked against the
+    oracle once and every rank's copy is tied to them.  At N > 1 the fused exchange is also checked against the
+    NCCL all-gather + merge path on the same local candidates."""
+    import torch
+    from oracle import c_oracle
+    keys_dev = db.knn2_keys_device(q_dev)
+    keys = keys_dev.cpu().numpy().view(np.uint64)
+    ok = True
+    if world > 1:
+        ref0 = keys_dev.clone()
+        dist.broadcast(ref0, src=0)
+        ok &= bool(torch.equal(ref0, keys_dev))
+        local = db.ops.local_knn2(q_dev, db.shard, db.row_lo)
+        merged = db.ops.merge(db.ops.all_gather(local, db.group))
+        ok &= bool(torch.equal(merged, keys_dev))
+    mine = np.arange(rank, query.shape[0], world)
+    threads = max(1, (os.cpu_count() or 8) // world)
+    ok &= bool(np.array_equal(keys[mine], c_oracle.knn2_keys(query[mine], train, threads=threads)))
+    t = torch.tensor([int(ok)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(int(t) == 1)
+
+
+def tensor_roofline(nat, peaks, peak_src, variant_used, nq, nt_local, kern_ms, batch=1):
+    """Roofline record of the dominant tensor-core kernel.  `frac` = achieved / (2 or 4 x MEASURED bf16 BURST) -- the
+    kernel is timed alone by its own event pair -- and `frac_of_mma_issue_peak` = achieved / the measured
+    tcgen05.mma issue loop of this chip (the tighter, architectural ceiling)."""
+    local_pairs = float(nq) * nt_local * batch
+    achieved = local_pairs * I8_OPS_PER_PAIR / (kern_ms * 1e-3) / 1e12
+    mult = 2.0 if variant_used == "i8" else 4.0
+    issue_peak, issue_src = mma_issue_peak(variant_used)
+    row_bytes = 256 if variant_used == "i8" else 128
+    kind = "kind::i8" if variant_used == "i8" else "kind::mxf4"
+    peak = mult * peaks["bf16_tflops"]
+    launch = nat.describe_launch(nq, nt_local, batch, variant_used)
+    tiles = 2.0 * (-(-nq // 256)) * (-(-nt_local // 128)) * batch     # 128 x 128 accumulator tiles
+    return {"bound": "tensor", "kernel": launch.split()[0], "launch": launch, "achieved": achieved, "peak": peak,
+            "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+            "note": f"+/-1 multiply-add ops (512/pair); peak = {mult:g} x bf16_tflops BURST of {peak_src} "
+                    f"({kind} issues at {mult:g}x the bf16 rate; the kernel is timed alone by its own event pair)",
+            "kernel_ms": kern_ms, "pairs_per_launch": local_pairs,
+            "frac_of_mma_issue_peak": achieved / issue_peak, "mma_issue_peak": issue_peak,
+            "mma_issue_peak_source": issue_src,
+            "frac_of_sustained_bf16_x": achieved / (mult * peaks["bf16_tflops_sustained"]),
+            "algorithmic_bytes": 32 * (nq + nt_local) * batch + 16 * nq * batch,
+            "operand_bytes": (nt_local + nq) * row_bytes * batch,
+            "hbm_gbs": (nt_local * row_bytes + nq * row_bytes) * batch / (kern_ms * 1e-3) / 1e9}
+
+
+def time_c4(db, q_dev, steps, warmup, barrier, nat, torch, local_rank):
+    """K timed steps, inputs resident: (ms per step, mean ms of the dominant kernel, clocks)."""
+    for _ in range(max(warmup, 3)):
+        db.knn2_keys_device(q_dev)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(steps):
+        nat.profile_events(*kern_ev[i])
+        db.knn2_keys_device(q_dev)
+    e1.record()
+    barrier()
+    nat.profile_events(None, None)
+    clocks = sampler.stop()
+    return e0.elapsed_time(e1) / steps, float(np.mean([a.elapsed_time(b) for a, b in kern_ev])), clocks
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -247,8 +369,6 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -260,54 +380,30 @@ def run_b200(args):
     query, train = make_c4()
     sizes = [KF_ROWS] * N_KEYFRAMES
     kf_lo, kf_hi, row_lo, row_hi = sx.shard_ranges(sizes, world)[rank]
-    local_kfs = [train[i * KF_ROWS:(i + 1) * KF_ROWS] for i in range(kf_lo, kf_hi)]
-    db = sx.ShardedKeyframeDatabase(sizes, local_kfs, rank=rank, world_size=world,
-                                    group=None if world == 1 else dist.group.WORLD, device=dev, variant=args.variant,
-                                    exchange=args.exchange)
-    del local_kfs
+
+    def build_db(train_rows):
+        local_kfs = [train_rows[i * KF_ROWS:(i + 1) * KF_ROWS] for i in range(kf_lo, kf_hi)]
+        return sx.ShardedKeyframeDatabase(sizes, local_kfs, rank=rank, world_size=world,
+                                          group=None if world == 1 else dist.group.WORLD, device=dev,
+                                          variant=args.variant, exchange=args.exchange)
+
+    db = build_db(train)
     q_dev = torch.from_numpy(query).to(dev)
     nt_local = row_hi - row_lo
     variant_used = nat.VARIANT_NAMES[db.shard["tc"]] if db.shard["prepared"] is not None else args.variant
 
-    # ---- correctness of what is timed (outside the timed region): sample of rows vs the oracle ----
     verified = None
     if not args.no_verify:
-        from oracle import c_oracle
-        keys = db.knn2_keys_device(q_dev).cpu().numpy().view(np.uint64)
-        if rank == 0:
-            sample = np.linspace(0, NQ - 1, 48).astype(np.int64)
-            verified = bool(np.array_equal(keys[sample], c_oracle.knn2_keys(query[sample], train)))
-            if not verified:
-                raise SystemExit("bench: GPU result differs from the oracle")
-
-    def step():
-        return db.knn2_keys_device(q_dev)
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
+        verified = verify_all_rows(db, q_dev, query, train, rank, world, dist, dev)
+        if not verified:
+            raise SystemExit("bench: GPU result differs from the oracle")
 
     # ---- timed region: K steps, inputs resident ---------------------------------------------------------
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    kern_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record()
-    for i in range(args.steps):
-        nat.profile_events(*kern_ev[i])
-        step()
-    e1.record()
-    barrier()
-    nat.profile_events(None, None)
-    clocks = sampler.stop()
-    ms_total = e0.elapsed_time(e1)
-    kern_ms = float(np.mean([a.elapsed_time(b) for a, b in kern_ev]))
-    t = torch.tensor([ms_total, kern_ms], dtype=torch.float64, device=dev)
+    ms_per_step, kern_ms, clocks = time_c4(db, q_dev, args.steps, args.warmup, barrier, nat, torch, local_rank)
+    t = torch.tensor([ms_per_step, kern_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, kern_ms_max = float(t[0]), float(t[1])
-    ms_per_step = ms_total / args.steps
+    ms_per_step, kern_ms_max = float(t[0]), float(t[1])
     total_pairs = float(NQ) * N_KEYFRAMES * KF_ROWS
     value = total_pairs / (ms_per_step * 1e-3) / 1e9
 
@@ -331,34 +427,16 @@ def run_b200(args):
     e2e_value = total_pairs / e2e_s / 1e9
 
     # ---- roofline of the dominant kernel (this rank's shard), from the live CUDA-event timing -----------
-    local_pairs = float(NQ) * nt_local
     if variant_used in ("i8", "f4"):
-        # 256 MAC = 512 ops per pair for both cores; kind::mxf4 issues them at twice the kind::i8 rate
-        achieved = local_pairs * I8_OPS_PER_PAIR / (kern_ms_max * 1e-3) / 1e12
-        mult = 2.0 if variant_used == "i8" else 4.0
-        issue_peak = 4569.0 if variant_used == "i8" else 8838.0
-        row_bytes = 256 if variant_used == "i8" else 128
-        kind = "kind::i8" if variant_used == "i8" else "kind::mxf4"
-        peak = mult * peaks["bf16_tflops_sustained"]
-        # shards whose CTAs see <= 1300 tiles run the *_floor twin of the kernel (shared row thresholds)
-        launch = nat.describe_launch(NQ, nt_local, 1, variant_used)
-        roofline = {"bound": "tensor", "kernel": launch.split()[0], "launch": launch, "achieved": achieved, "peak": peak,
-                    "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                    "note": f"+/-1 multiply-add ops (512/pair); peak = {mult:g} x bf16_tflops_sustained of {peak_src} "
-                            f"({kind} issues at {mult:g}x the bf16 rate)",
-                    "kernel_ms": kern_ms_max, "pairs_per_launch": local_pairs,
-                    "frac_of_mma_issue_peak": achieved / issue_peak,
-                    "mma_issue_peak_note": f"{issue_peak:g} TOP/s = tcgen05.mma {kind} issue loop at 1965 MHz "
-                                           "(tools/microbench.cu, tools/microbench_fp4.cu, profiles/r01*_microbench*.json)",
-                    "hbm_gbs": (nt_local * row_bytes + NQ * row_bytes) / (kern_ms_max * 1e-3) / 1e9}
+        roofline = tensor_roofline(nat, peaks, peak_src, variant_used, NQ, nt_local, kern_ms_max)
     else:
         sm = nat.sm_count()
-        achieved = local_pairs * POPC_PER_PAIR / (kern_ms_max * 1e-3) / 1e12
+        achieved = float(NQ) * nt_local * POPC_PER_PAIR / (kern_ms_max * 1e-3) / 1e12
         peak = sm * 16 * peaks["sm_max_mhz"] * 1e6 / 1e12
         roofline = {"bound": "popc", "kernel": "hm_popc_knn2_kernel", "achieved": achieved, "peak": peak,
                     "unit": "Tpopc/s", "frac": achieved / peak, "traffic": None,
                     "note": "POPC issue roofline: 8 POPC per pair; peak = SMs x 16/clk (measured 15.7) x sm_max_mhz",
-                    "kernel_ms": kern_ms_max, "pairs_per_launch": local_pairs}
+                    "kernel_ms": kern_ms_max, "pairs_per_launch": float(NQ) * nt_local}
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(traffic_file):
         try:
@@ -371,18 +449,60 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "config": dict(c4_config(world), variant=variant_used, exchange=db.exchange_mode,
+                                                         exchange_fallback_reason=db.exchange_fallback_reason,
+                                                         distribution="M (matchable queries, uniform database)",
                                                          db_format={"i8": "train shard resident as +/-1 int8 (expanded once at add())",
                                                                     "f4": "train shard resident as +/-1 e2m1 (expanded once at add())"}.get(variant_used, "packed bits")),
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": NQ * 32, "d2h_bytes_per_step": NQ * 16,
                 "ms_per_step": e2e_s * 1e3, "api": "ShardedKeyframeDatabase.knnMatch(query_numpy, 2) -> DMatch tuples",
                 "arrays_out_ms_per_step": e2e_arr_s * 1e3},
-        # per step: hm_prepare*_kernel (query expansion) + the k-NN kernel (split merge and, for N > 1, the fused
-        # exchange run inside it); with the NCCL exchange one hm_merge_top2_kernel more (ncu launch list in profiles/)
-        "gpu_launches": args.steps * (2 if world == 1 or db.exchange_mode == "fused" else 3),
+        # per step: the k-NN kernel (query expansion, split merge and, for N > 1, the fused exchange run inside it);
+        # with the NCCL exchange one hm_merge_top2_kernel more (ncu launch list in profiles/)
+        "gpu_launches": args.steps * db.ops.launches_per_step(db.shard, world, db.exchange_mode),
         "roofline": roofline,
         "verified_vs_oracle": verified,
+        "verified_rows": NQ if verified else 0,
+        "verified_how": "all rows vs the C oracle (rows split over ranks), every rank bit-identical to rank 0"
+                        + (", fused exchange == NCCL all-gather + merge" if world > 1 else ""),
     }
+
+    if world == 1 and not args.quick:
+        # ---- north star: "report both" -- the same workload on uniform queries and on the adversarial monotone input
+        others = {}
+        del db
+        for name in ("U", "monotone"):
+            q2, t2 = make_c4(dist=name)
+            db2 = build_db(t2)
+            q2_dev = torch.from_numpy(q2).to(dev)
+            from oracle import c_oracle
+            rows = np.linspace(0, NQ - 1, 250).astype(np.int64)
+            got = db2.knn2_keys_device(q2_dev).cpu().numpy().view(np.uint64)
+            good = bool(np.array_equal(got[rows], c_oracle.knn2_keys(q2[rows], t2)))
+            if not good:
+                raise SystemExit(f"bench: C4 distribution {name}: GPU result differs from the oracle")
+            ms2, k2, _ = time_c4(db2, q2_dev, max(10, args.steps // 4), 3, barrier, nat, torch, local_rank)
+            others[name] = {"value": total_pairs / (ms2 * 1e-3) / 1e9, "unit": UNIT, "ms_per_step": ms2, "kernel_ms": k2,
+                            "verified_rows": int(rows.size)}
+            del db2, q2_dev, t2
+            torch.cuda.empty_cache()
+        line["distributions"] = dict(others, M={"value": value, "unit": UNIT, "ms_per_step": ms_per_step,
+                                                "kernel_ms": kern_ms_max, "verified_rows": NQ})
+        # ---- the other BASELINE.json configs as sub-records of this one driver-run line ------------------------
+        from tools import bench_extra
+        subs = {}
+        sub_steps = max(10, min(args.steps, 30))
+        for key, wl, n in (("c1", "c1", 0), ("c2", "c2", 0), ("c3_16k", "c3", 16384), ("c3_64k", "c3", 65536), ("c5", "c5", 0)):
+            try:
+                rec = bench_extra.measure(wl, sub_steps, 3, args.variant, n, cpu_seconds=3.0)
+                subs[key] = {k: rec[k] for k in ("value", "unit", "ms_per_step", "config", "e2e", "roofline", "cpu_baseline",
+                                                 "verified_vs_oracle", "verified", "gpu_launches", "frame_pairs_per_s")
+                             if k in rec}
+            except SystemExit as e:      # a parity failure in a sub-config fails the bench
+                raise
+            except Exception as e:       # anything else is reported, not hidden
+                subs[key] = {"error": f"{type(e).__name__}: {e}"}
+        line["configs"] = subs
 
     # ---- cpu baseline beside it (rank 0, N=1 only): cv2 on the host cores, bounded sample ----------------
     if world == 1 and not args.no_cpu_baseline:
@@ -415,6 +535,7 @@ def main():
     ap.add_argument("--n", type=int, default=65536, help="c3: N x N")
     ap.add_argument("--exchange", default="auto", choices=["auto", "fused", "nccl"])
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="C4 only: skip the other distributions and the c1/c2/c3/c5 sub-records")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

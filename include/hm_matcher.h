@@ -78,6 +78,10 @@ typedef enum hm_variant {
 #define HM_FLAG_RATIO 1u          /* Lowe ratio test: keep iff d1 < ratio_lut[d2] (needs 2 neighbours) */
 #define HM_FLAG_MUTUAL 2u         /* cross-check: keep iff q is t's best query too (cv2 crossCheck=True) */
 #define HM_FLAG_DIST_THRESHOLD 4u /* reference filter: d < max(2*min_d, thr), feature_matchers.py:41-43 */
+/* Combination rule: the three tests are independent predicates on a query row's forward neighbours, and a match is
+ * kept iff every requested one holds.  min_d of the distance filter is taken over ALL forward best matches (what
+ * feature_matchers.py:41 sees: the reference's matcher has crossCheck=False and no ratio test), not over the
+ * survivors of RATIO / MUTUAL; the reference itself never combines them (tested: test_fused_pipeline_and_batched_vs_oracle, case ratio 0.9 + mutual + thr 64.5). */
 
 /* ---- introspection ------------------------------------------------------------------ */
 HM_API int hm_version(void);

@@ -456,6 +456,10 @@ HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, in
     int rc = device_info(&di);
     if (rc != HM_OK) return rc;
     if (batch <= 0) return HM_OK;
+    if (!out_count || (nq > 0 && (!out_q || !out_t || !out_d))) {      // before anything is enqueued
+        set_error("hm_match_fused: null output");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     RatioLut lut;
     int thr;
@@ -487,10 +491,6 @@ HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, in
         r.q_batch_stride = t_batch_stride; r.t_batch_stride = q_batch_stride; r.batch = batch;
         r.top1 = true;                       // the filter only reads each train row's best query
         if ((rc = knn2_dispatch(r, bwd, variant, knn_ws, knn_ws_bytes, st)) != HM_OK) return rc;
-    }
-    if (!out_count || (nq > 0 && (!out_q || !out_t || !out_d))) {
-        set_error("hm_match_fused: null output");
-        return HM_ERR_INVALID_ARGUMENT;
     }
     return launch_filter(fwd, nq, bwd, nt, batch, flags, lut, thr, out_q, out_t, out_d, out_count, st);
 }
@@ -808,8 +808,9 @@ HM_API int hm_frame_put(hm_context* ctx, int slot, const uint8_t* desc_host, int
         return HM_ERR_INVALID_ARGUMENT;
     }
     FrameSlot& f = ctx->slots[slot];
-    f.n = n;
-    f.has_points = points_host != nullptr;
+    // the slot advertises rows only once their copy is enqueued: a failed allocation below leaves it empty
+    f.n = 0;
+    f.has_points = false;
     if (n == 0) return HM_OK;
     const size_t bytes = slot_points_offset(n) + (size_t)n * 8;
     if (f.cap < bytes) {
@@ -818,7 +819,13 @@ HM_API int hm_frame_put(hm_context* ctx, int slot, const uint8_t* desc_host, int
         if (f.h) cudaFreeHost(f.h);
         f.d = f.h = nullptr; f.cap = f.h_cap = 0;
         HM_CUDA_CHECK(cudaMalloc(&f.d, bytes + bytes / 2));
-        HM_CUDA_CHECK(cudaMallocHost(&f.h, bytes + bytes / 2));
+        if (cudaMallocHost(&f.h, bytes + bytes / 2) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(f.d);
+            f.d = f.h = nullptr;
+            set_error("hm_frame_put: cudaMallocHost(%zu) failed", bytes + bytes / 2);
+            return HM_ERR_CUDA;
+        }
         f.cap = f.h_cap = bytes + bytes / 2;
     }
     if (!f.uploaded) HM_CUDA_CHECK(cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
@@ -832,6 +839,8 @@ HM_API int hm_frame_put(hm_context* ctx, int slot, const uint8_t* desc_host, int
     // stream order also keeps earlier matches that read this slot ahead of the overwrite
     HM_CUDA_CHECK(cudaMemcpyAsync(f.d, f.h, copy_bytes, cudaMemcpyHostToDevice, ctx->stream));
     HM_CUDA_CHECK(cudaEventRecord(f.uploaded, ctx->stream));
+    f.n = n;
+    f.has_points = points_host != nullptr;
     return HM_OK;
 }
 

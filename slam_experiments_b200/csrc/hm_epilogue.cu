@@ -192,8 +192,10 @@ int launch_exchange_merge(const unsigned long long* local_keys, int local_groups
     int rc = fill_exchange_args(&P.x, world, rank, peers, max_rows, epoch, rows);
     if (rc != HM_OK) return rc;
     P.local = local_keys; P.local_groups = local_groups; P.out = out; P.rows = rows;
-    // the grid covers max_rows (not just rows) so that every rank runs the same CTAs and flags
-    hm_exchange_merge_kernel<<<(unsigned)exchange_blocks(max_rows), kExchangeRows, 0, stream>>>(P);
+    // One CTA and one flag per 256-row block that holds rows.  `rows` is the replicated query's size, identical on
+    // every rank, and the k-NN kernel's fused exchange uses the same blocks: ranks may mix the two kernels (a rank
+    // without a prepared shard runs this one) and still post / wait on exactly the same flags.
+    hm_exchange_merge_kernel<<<(unsigned)ceil_div(rows, kExchangeRows), kExchangeRows, 0, stream>>>(P);
     HM_CUDA_CHECK(cudaGetLastError());
     return HM_OK;
 }

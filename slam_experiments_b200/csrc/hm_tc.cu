@@ -38,6 +38,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <mutex>
+
 #include "hm_common.cuh"
 #include "hm_tcgen05.cuh"
 
@@ -656,7 +658,9 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             ulonglong2 k = make_ulonglong2(kNoMatch, kNoMatch);
             if (has_row) fold_partials(P.out, P.splits, P.out_split_stride, (long long)b * P.nq + row, k.x, k.y);
             // sharded database: push to the peer GPUs, wait for theirs, merge -- still inside this launch
-            if (P.xch.world > 1) k = exchange_and_merge(P.xch, row, has_row, k, qb);
+            // (only query blocks that hold rows take part: hm_exchange_merge_kernel on a peer covers exactly
+            // ceil(nq / 256) blocks, so both kernels post and wait on the same flags whatever mix of them the ranks run)
+            if (P.xch.world > 1 && (long long)qb * kBlockM < P.nq) k = exchange_and_merge(P.xch, row, has_row, k, qb);
             if (has_row) *reinterpret_cast<ulonglong2*>(P.final_out + ((long long)b * P.nq + row) * 2) = k;
         }
     }
@@ -718,15 +722,48 @@ int cluster_override()
     return v;
 }
 
+// Per-device launch state.  cudaFuncSetAttribute (the > 48 KB dynamic shared memory opt-in) and cluster occupancy
+// are per DEVICE, and one process may drive several devices (BFMatcher(device=...), FrameDescriptorStore(device=...)),
+// from several threads: both caches are keyed by the device ordinal and guarded by one mutex.
+constexpr int kMaxDevices = 64;
+std::mutex g_launch_state_mu;
+
+int current_device_slot()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+    return (dev >= 0 && dev < kMaxDevices) ? dev : -1;      // -1: do not cache
+}
+
+template <class C>
+cudaError_t ensure_smem_opt_in()
+{
+    static bool done[kMaxDevices] = {};
+    const int dev = current_device_slot();
+    std::lock_guard<std::mutex> lock(g_launch_state_mu);
+    if (dev >= 0 && done[dev]) return cudaSuccess;
+    for (int mode = 0; mode < 3; ++mode) {
+        const cudaError_t e = cudaFuncSetAttribute(kernel_of<C>(mode), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>());
+        if (e != cudaSuccess) return e;
+    }
+    if (dev >= 0) done[dev] = true;
+    return cudaSuccess;
+}
+
 // CTAs that can be co-resident when launched as clusters of `cs` (1 CTA per SM; clusters of 4 cannot
-// use every SM of every GPC).  Queried once per cluster size; falls back to the SM count.
+// use every SM of every GPC).  Queried once per device and cluster size; falls back to the SM count.
 template <class C>
 int resident_ctas(int cs, int sm_count)
 {
-    static int cache[5] = {0, 0, 0, 0, 0};
-    if (cache[cs]) return cache[cs];
+    static int cache[kMaxDevices][5] = {};
+    if (cs <= 1) return sm_count;
+    const int dev = current_device_slot();
+    if (dev >= 0) {
+        std::lock_guard<std::mutex> lock(g_launch_state_mu);
+        if (cache[dev][cs]) return cache[dev][cs];
+    }
     int v = sm_count;
-    if (cs > 1) {
+    if (ensure_smem_opt_in<C>() == cudaSuccess) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(cs * 64, 1, 1);
         cfg.blockDim = dim3(threads<C>());
@@ -739,13 +776,15 @@ int resident_ctas(int cs, int sm_count)
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         int n = 0;
-        if (cudaFuncSetAttribute(kernel_of<C>(), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()) == cudaSuccess &&
-            cudaOccupancyMaxActiveClusters(&n, kernel_of<C>(), &cfg) == cudaSuccess && n > 0)
-            v = n * cs;
-        else
-            cudaGetLastError();
+        if (cudaOccupancyMaxActiveClusters(&n, kernel_of<C>(), &cfg) == cudaSuccess && n > 0) v = n * cs;
+        else cudaGetLastError();
+    } else {
+        cudaGetLastError();
     }
-    cache[cs] = v;
+    if (dev >= 0) {
+        std::lock_guard<std::mutex> lock(g_launch_state_mu);
+        cache[dev][cs] = v;
+    }
     return v;
 }
 
@@ -812,12 +851,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
                     int sm_count, cudaStream_t stream, const unsigned long long** out_partials,
                     int* out_groups, const ExchangeArgs* exchange, bool top1 = false)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        for (int mode = 0; mode < 3; ++mode)
-            HM_CUDA_CHECK(cudaFuncSetAttribute(kernel_of<C>(mode), cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<C>()));
-        attr_set = true;
-    }
+    HM_CUDA_CHECK(ensure_smem_opt_in<C>());
     const TcPlan pl = plan_tc<C>(nq, nt, batch, sm_count);
     if ((long long)pl.ntiles * C::kTileN > (1ll << 32)) {
         set_error("train set too large for 32-bit trainIdx");

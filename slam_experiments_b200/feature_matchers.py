@@ -110,17 +110,29 @@ def _build_dmatches(q, t, d, img=0, rows: int = 0):
 
 
 class _Staging:
-    """Pinned host buffers reused across calls (H2D / D2H without pageable-memory syncs)."""
+    """Pinned host buffers reused across calls (H2D / D2H without pageable-memory syncs).
+
+    An H2D out of a pinned buffer is asynchronous: callers such as ``BFMatcher.knn_keys_device`` return
+    unsynchronised device tensors, so the next call may arrive while the copy is still queued behind running
+    kernels.  Every buffer therefore carries the event of its last H2D, and the next host write waits for it
+    (the C path, ``hm_frame_put``, guards its staging buffers the same way)."""
 
     def __init__(self):
         self._pin = {}
+        self._h2d_done = {}
 
     def pinned(self, key: str, nbytes: int) -> torch.Tensor:
         buf = self._pin.get(key)
         if buf is None or buf.numel() < nbytes:
+            self.wait(key)                           # the old buffer may still feed a queued copy
             buf = torch.empty(max(nbytes, 4096), dtype=torch.uint8).pin_memory()
             self._pin[key] = buf
         return buf
+
+    def wait(self, key: str) -> None:
+        ev = self._h2d_done.get(key)
+        if ev is not None:
+            ev.synchronize()
 
     def to_device(self, key: str, arr: np.ndarray, device: torch.device) -> torch.Tensor:
         n = arr.shape[0]
@@ -128,8 +140,14 @@ class _Staging:
         if nbytes == 0:
             return torch.empty((0, nat.DESC_BYTES), dtype=torch.uint8, device=device)
         host = self.pinned(key, nbytes)[:nbytes].view(n, nat.DESC_BYTES)
+        self.wait(key)                               # the previous H2D has left this buffer
         host.numpy()[...] = arr                      # one memcpy, handles strided views
-        return host.to(device, non_blocking=True)
+        out = host.to(device, non_blocking=True)
+        ev = self._h2d_done.get(key)
+        if ev is None:
+            ev = self._h2d_done[key] = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        return out
 
     def to_host(self, key: str, t: torch.Tensor) -> np.ndarray:
         """D2H through pinned memory; synchronises the current stream."""

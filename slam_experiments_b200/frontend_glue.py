@@ -130,14 +130,7 @@ class FrameDescriptorStore:
         if self._ctx is None:
             with nat.on_device(self.device):
                 self._ctx = nat.HostContext()
-        if frame_id in self._slots:
-            slot = self._slots.pop(frame_id)[0]
-        else:
-            if not self._free_slots:                               # evict the oldest resident frame
-                _, (slot, _, _) = self._slots.popitem(last=False)
-            else:
-                slot = self._free_slots.pop()
-        pos = None
+        pos = None                                                 # validate before any slot changes hands
         if positions is not None:
             pos = np.asarray(positions)
             if pos.size == 0:
@@ -145,8 +138,18 @@ class FrameDescriptorStore:
             if pos.ndim != 2 or pos.shape[1] != 2 or pos.shape[0] != a.shape[0]:
                 raise MatcherError(f"positions: expected [{a.shape[0]}, 2], got {pos.shape}")
             pos = pos.astype(np.int32, copy=False)
-        with nat.on_device(self.device):
-            self._ctx.frame_put(slot, a, pos)
+        if frame_id in self._slots:
+            slot = self._slots.pop(frame_id)[0]
+        elif self._free_slots:
+            slot = self._free_slots.pop()
+        else:                                                      # evict the oldest resident frame
+            _, (slot, _, _) = self._slots.popitem(last=False)
+        try:
+            with nat.on_device(self.device):
+                self._ctx.frame_put(slot, a, pos)
+        except Exception:
+            self._free_slots.append(slot)                          # the slot is empty again (hm_frame_put clears it)
+            raise
         self._slots[frame_id] = (slot, a.shape[0], pos is not None)
         if frame_id in self._frames:
             del self._frames[frame_id]

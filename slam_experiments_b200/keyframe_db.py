@@ -124,6 +124,16 @@ class NativeOps:
                                           variant=shard["tc"])
         return nat.knn2_keys(query, shard["bits"], train_base=train_base, variant=self.variant)
 
+    def launches_per_step(self, shard, world: int, exchange_mode: str) -> int:
+        """Kernels of THIS library launched per ``knn2_keys_device`` call (bench.py's ``gpu_launches``; the ncu launch
+        lists under profiles/ are the evidence): query expansion + k-NN for a prepared shard (the split merge and the
+        fused exchange run inside the k-NN kernel), k-NN (+ split merge) for packed bits, + hm_exchange_merge or
+        hm_merge_top2 when the exchange is a launch of its own."""
+        n = 2 if shard["prepared"] is not None else 2
+        if world > 1 and (exchange_mode != "fused" or shard["prepared"] is None or self.exchange_kernel != "in_knn"):
+            n += 1
+        return n
+
     def all_gather(self, keys: torch.Tensor, group) -> torch.Tensor:
         import torch.distributed as dist
         world = dist.get_world_size(group)
@@ -161,10 +171,18 @@ class NativeOps:
             return "nccl"
 
     def local_knn2_exchange(self, query: torch.Tensor, shard, train_base: int, group) -> torch.Tensor:
-        """Local k-NN + exchange + merge: one k-NN launch (plus the query expansion) per step."""
+        """Local k-NN + exchange + merge: one k-NN launch (plus the query expansion) per step.
+
+        Which kernel carries the exchange is a per-rank choice (a rank whose shard has no prepared image -- empty,
+        or below the tensor-core threshold under variant="auto" -- runs ``hm_exchange_merge`` after a plain k-NN).
+        That is safe because both kernels use the same symmetric buffer, epoch and flag blocks (one per 256 query
+        rows that exist); whether the symmetric path is used at all depends only on ``_xch`` (set up collectively)
+        and on the query size (replicated), so every rank takes the same branch here."""
         x = getattr(self, "_xch", None)
         nq = query.shape[0]
-        if x is None or shard["prepared"] is None or not (0 < nq <= x["max_rows"]):
+        if x is None or not (0 < nq <= x["max_rows"]):
+            return self.merge(self.all_gather(self.local_knn2(query, shard, train_base), group))
+        if shard["prepared"] is None:
             return self.gather_merge(self.local_knn2(query, shard, train_base), group)
         qprep = nat.prepare(query, variant=shard["tc"])
         x["epoch"] += 1
@@ -219,10 +237,17 @@ class ShardedKeyframeDatabase:
         self.shard = self.ops.make_shard(self.ops.upload(cat))
         # exchange step: "fused" = hm_exchange_merge over symmetric memory, "nccl" = all-gather + merge
         self.exchange_mode = "none" if world_size == 1 else "nccl"
+        # why "auto" ended up on the NCCL path (None = it did not): surfaced in bench.py's config so that a broken
+        # symmetric-memory setup cannot silently cost the fused path's throughput
+        self.exchange_fallback_reason = None
         if world_size > 1 and exchange in ("auto", "fused") and hasattr(self.ops, "setup_exchange"):
             self.exchange_mode = self.ops.setup_exchange(group, world_size, rank, max_query_rows)
-            if exchange == "fused" and self.exchange_mode != "fused":
-                raise nat.NativeError(f"fused exchange unavailable: {getattr(self.ops, '_xch_error', '?')}")
+            if self.exchange_mode != "fused":
+                self.exchange_fallback_reason = getattr(self.ops, "_xch_error", "unknown")
+                if exchange == "fused":
+                    raise nat.NativeError(f"fused exchange unavailable: {self.exchange_fallback_reason}")
+                import warnings
+                warnings.warn(f"fused exchange unavailable, using the NCCL all-gather path: {self.exchange_fallback_reason}")
 
     # ---- incremental growth (Map.insert_keyframe, `/root/reference/backend.py:31-37`) -----------------
     def append_keyframe(self, descriptors: np.ndarray) -> int:

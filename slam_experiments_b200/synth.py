@@ -69,3 +69,15 @@ def local_window(n_frames: int = 32, rows: int = 10000, seed: int = 3200):
     train = rng.integers(0, 256, (n_frames, rows, DESC_BYTES), dtype=np.uint8)
     query = np.stack([matchable_queries(train[i], rows, seed + 1 + i) for i in range(n_frames)])
     return query, train
+
+
+def euroc_shaped_sequence() -> np.ndarray:
+    """C2 on the SURVEY.md 8(d) input: 100 frames of 752 x 480 (`/root/reference/1.png` resized, warped along a smooth
+    seeded homography trajectory, Gaussian noise sigma 2), 2000 REAL ORB descriptors per frame from the reference's
+    own detector.  The images are not available on the GPU box, so the descriptors are a committed fixture
+    (tests/golden/c2_sequence_orb2000.npz, written by tests/golden/make_golden_orb.py).  [100, 2000, 32] uint8."""
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden",
+                        "c2_sequence_orb2000.npz")
+    with np.load(path) as z:
+        return np.ascontiguousarray(z["descriptors"])

@@ -27,7 +27,7 @@ def load_golden(path):
 
 def pair_goldens():
     """Every fixture recording a (query, train) problem."""
-    return [p for p in golden_files() if "collection" not in os.path.basename(p)]
+    return [p for p in golden_files() if "collection" not in os.path.basename(p) and "sequence" not in os.path.basename(p)]
 
 
 @pytest.fixture(scope="session")

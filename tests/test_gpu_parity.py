@@ -334,3 +334,125 @@ def test_host_calls_replay_cuda_graphs_with_fresh_data():
             assert np.array_equal(gq, eq) and np.array_equal(gt, et) and np.array_equal(gd, ed)
             assert np.array_equal(pq, pos_q[eq]) and np.array_equal(pt, pos_t[et])
     ctx.close()
+
+
+# =====================================================================================================
+# BASELINE.json full-size configs, every row against the oracle
+# =====================================================================================================
+def _c4_database(kind):
+    """2000 queries x 4096 keyframes x 2000 rows (C4).  At N=1 every CTA of the tensor-core kernels sees
+    1730 tiles, i.e. runs the late refresh cadence of the shared row thresholds (tiles >= 512)."""
+    if kind == "uniform":                      # the bench's own input
+        return synth.keyframe_database(4096, 2000, 2000, seed=4096)
+    rng = np.random.default_rng(4097)
+    nt, nq = 4096 * 2000, 2000
+    if kind == "dups":
+        # 64 pool rows, each planted ~1280 times all over the database: the best distance of every query is
+        # tied across hundreds of CTAs and across early and late tiles -> the two LOWEST copies must win
+        t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        pool = rng.integers(0, 256, (64, 32), dtype=np.uint8)
+        where = rng.choice(nt, 64 * 1280, replace=False)
+        t[where] = pool[rng.integers(0, 64, where.size)]
+        q = pool[rng.integers(0, 64, nq)].copy()
+        flips = rng.integers(0, 4, nq)
+        for i in range(nq):
+            for b in rng.choice(256, flips[i], replace=False):
+                q[i, b >> 3] ^= 1 << (b & 7)
+        return q, t
+    # "lowentropy": every byte in {0, 1, 2}: a handful of distinct distances, ties everywhere, the exact
+    # insertion path of the scan runs for most chunks of every tile
+    return rng.integers(0, 3, (nq, 32), dtype=np.uint8), rng.integers(0, 3, (nt, 32), dtype=np.uint8)
+
+
+@pytest.fixture(scope="module", params=("uniform", "dups", "lowentropy"))
+def c4_case(request):
+    q, t = _c4_database(request.param)
+    return request.param, q, t, co.knn2_keys(q, t)
+
+
+@pytest.mark.parametrize("variant", ("f4", "i8"))
+def test_full_c4_all_rows_vs_oracle(c4_case, variant):
+    """Full C4 at N=1, all 2000 rows bit-exact, through the resident (prepared) database path bench.py times."""
+    kind, q, t, expect = c4_case
+    if kind == "lowentropy" and variant == "i8":
+        pytest.skip("covered by f4; keeps the suite short")
+    td = dev(t)
+    tp = nat.prepare(td, variant=variant)
+    got = nat.knn2_keys_prepared(nat.prepare(dev(q), variant=variant), q.shape[0], tp, t.shape[0], 0, variant=variant)
+    got = got.cpu().numpy().view(np.uint64)
+    launch = nat.describe_launch(2000, t.shape[0], 1, variant)
+    assert int(launch.split("tiles_per_cta=")[1]) > 512 and "_floor" in launch, launch   # the late-cadence branch runs
+    bad = np.flatnonzero((got != expect).any(axis=1))
+    assert bad.size == 0, f"{kind}/{variant}: {bad.size} rows differ, first {bad[:5]}"
+    if kind == "dups":
+        idx, dist, _ = nat.split_keys(got)
+        assert (dist[:, 0] <= 3).all() and (idx[:, 0] < idx[:, 1]).all()
+
+
+def test_full_c4_popc_sample_and_dropin(c4_case):
+    """The POPC core on the full database (every 8th row, it is 25x slower) and the cv2-shaped collection API on top
+    of the same keys: (imgIdx, trainIdx) decoding of global rows."""
+    kind, q, t, expect = c4_case
+    if kind != "uniform":
+        pytest.skip("one database is enough for the slow core")
+    got = gpu_keys(q[::8], t, "popc")
+    assert np.array_equal(got, expect[::8])
+    db = sx.ShardedKeyframeDatabase([2000] * 4096, [t[i * 2000:(i + 1) * 2000] for i in range(4096)])
+    img, loc, d = db.knn_tensors(q, 2)
+    gidx, gdist, _ = nat.split_keys(expect)
+    assert np.array_equal(img, gidx // 2000) and np.array_equal(loc, gidx % 2000) and np.array_equal(d, gdist)
+
+
+def test_full_c5_window_pipeline_vs_oracle():
+    """Full C5: 32 problems of 10k x 10k, knnMatch k=2 -> ratio 0.75 -> mutual cross-check; q, t and distance
+    of every surviving match of every problem, and the forward keys."""
+    qs, ts = synth.local_window(32, 10000)
+    qd, td = dev(qs), dev(ts)
+    for variant in ("f4", "i8"):
+        oq, ot, od, cnt = nat.match_fused(qd, td, ratio=0.75, cross_check=True, variant=variant)
+        oq, ot, od, cnt = oq.cpu().numpy(), ot.cpu().numpy(), od.cpu().numpy(), cnt.cpu().numpy()
+        for i in range(32):
+            eq, et, ed = co.pipeline(qs[i], ts[i], 0.75, True)
+            n = int(cnt[i])
+            assert n == len(eq), (variant, i)
+            assert np.array_equal(oq[i, :n], eq) and np.array_equal(ot[i, :n], et) and np.array_equal(od[i, :n], ed), (variant, i)
+    keys = nat.knn2_keys_batched(qd, td, variant="f4").cpu().numpy().view(np.uint64)
+    for i in (0, 13, 31):
+        assert np.array_equal(keys[i], co.knn2_keys(qs[i], ts[i]))
+
+
+def test_c2_real_orb_sequence():
+    """C2 on the SURVEY 8(d) input: 100 warped 752 x 480 frames with real ORB descriptors (bit density 0.54,
+    correlated rows).  All 99 consecutive problems, batched and one by one through the drop-in, against the
+    oracle; three of them against the recorded output of the reference's matcher."""
+    g = load_golden(golden_files("c2_sequence_orb2000.npz")[0])
+    frames = g["descriptors"]
+    assert frames.shape == (100, 2000, 32) and (g["counts"] == 2000).all()
+    fd = dev(frames)
+    for variant in VARIANTS:
+        keys = nat.knn2_keys_batched(fd[1:], fd[:-1], variant=variant).cpu().numpy().view(np.uint64)
+        for i in range(99):
+            assert np.array_equal(keys[i], co.knn2_keys(frames[i + 1], frames[i])), (variant, i)
+    m = sx.BruteForceFeatureMatcher(norm_type=cv2.NORM_HAMMING)
+    for i in (0, 37, 98):
+        out = m.match(frames[i], frames[i + 1])                   # frontend.py:181-187
+        assert _rows(out) == [tuple(r) for r in g[f"ref_match_{i}"].tolist()]
+    pm = sx.BruteForceFeatureMatcher(norm_type=cv2.NORM_HAMMING, ratio=0.75, cross_check=True)
+    for i in (5, 60):
+        eq, et, ed = co.pipeline(frames[i + 1], frames[i], 0.75, True)
+        assert [(x.queryIdx, x.trainIdx, int(x.distance)) for x in pm.match(frames[i], frames[i + 1])] == \
+            list(zip(eq.tolist(), et.tolist(), ed.tolist()))
+
+
+def test_back_to_back_uploads_do_not_alias_staging():
+    """Two unsynchronised device-level calls in a row: the second call's host copy must not overwrite the
+    pinned staging buffer while the first call's H2D is still queued."""
+    bf = sx.BFMatcher(cv2.NORM_HAMMING)
+    rng = np.random.default_rng(3)
+    t = rng.integers(0, 256, (60000, 32), dtype=np.uint8)
+    qa = rng.integers(0, 256, (3000, 32), dtype=np.uint8)
+    qb = rng.integers(0, 256, (3000, 32), dtype=np.uint8)
+    ka = bf.knn_keys_device(qa, t)
+    kb = bf.knn_keys_device(qb, t)
+    assert np.array_equal(ka.cpu().numpy().view(np.uint64), co.knn2_keys(qa, t))
+    assert np.array_equal(kb.cpu().numpy().view(np.uint64), co.knn2_keys(qb, t))
