@@ -348,6 +348,12 @@ def time_c4(db, q_dev, steps, warmup, barrier, nat, torch, local_rank):
     barrier()
     nat.profile_events(None, None)
     clocks = sampler.stop()
+    # what the SMs really ran at: the k-NN kernel's first CTA stamps %globaltimer and clock64 at entry and exit (NVML,
+    # polled every few ms, reports the application clock even while the chip holds the tensor pipe at a lower one)
+    probe = nat.clock_probe(q_dev.device)
+    if probe:
+        clocks["sm_mhz_effective_in_kernel"] = probe["sm_mhz_effective"]
+        clocks["effective_note"] = "clock64 / %globaltimer over the first CTA of the last timed k-NN launch"
     return e0.elapsed_time(e1) / steps, float(np.mean([a.elapsed_time(b) for a, b in kern_ev])), clocks
 
 
@@ -429,6 +435,11 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (this rank's shard), from the live CUDA-event timing -----------
     if variant_used in ("i8", "f4"):
         roofline = tensor_roofline(nat, peaks, peak_src, variant_used, NQ, nt_local, kern_ms_max)
+        eff = clocks.get("sm_mhz_effective_in_kernel")
+        if eff:
+            roofline["frac_of_mma_issue_peak_at_effective_clock"] = roofline["achieved"] / (roofline["mma_issue_peak"] * eff / 1965.0)
+            roofline["effective_clock_note"] = (f"the issue peak is quoted at 1965 MHz; under this kernel the SMs ran at {eff:.0f} MHz "
+                                                "(clocks.sm_mhz_effective_in_kernel)")
     else:
         sm = nat.sm_count()
         achieved = float(NQ) * nt_local * POPC_PER_PAIR / (kern_ms_max * 1e-3) / 1e12

@@ -56,6 +56,10 @@ extern "C" {
 #define HM_DEFAULT_TENSOR_VARIANT 3
 /* prepared images are padded to whole tiles of this many rows */
 #define HM_PREPARED_TILE_ROWS 256
+/* Measurement aid: the tensor-core k-NN kernels leave four int64 at this byte offset of the workspace they were given --
+ * %globaltimer (ns) and clock64 (SM cycles) of their first CTA at entry and at exit.  (cycles / ns) is the SM clock the
+ * kernel really ran at; bench.py reports it next to NVML's figure.  Not part of the data path. */
+#define HM_WS_CLOCK_PROBE_OFFSET 64
 
 typedef enum hm_status {
     HM_OK = 0,

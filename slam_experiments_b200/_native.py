@@ -184,6 +184,25 @@ def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
     return buf
 
 
+WS_CLOCK_PROBE_OFFSET = 64      # HM_WS_CLOCK_PROBE_OFFSET
+
+
+def clock_probe(device) -> Optional[dict]:
+    """SM clock the last tensor-core k-NN kernel on this thread / stream really ran at: the kernel's first CTA stamps
+    %globaltimer and clock64 at entry and exit into its workspace header (``HM_WS_CLOCK_PROBE_OFFSET``).  Synchronises.
+    Returns ``{"sm_mhz_effective", "cta0_us"}`` or None when no such kernel has run on the cached workspace."""
+    device = torch.device(device)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, threading.get_ident())
+    buf = _ws_cache.get(key)
+    if buf is None:
+        return None
+    vals = buf[WS_CLOCK_PROBE_OFFSET:WS_CLOCK_PROBE_OFFSET + 32].cpu().numpy().view(np.int64)
+    ns, cyc = int(vals[2] - vals[0]), int(vals[3] - vals[1])
+    if ns <= 0 or cyc <= 0:
+        return None
+    return {"sm_mhz_effective": cyc / ns * 1e3, "cta0_us": ns / 1e3}
+
+
 def _stream_ptr(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 

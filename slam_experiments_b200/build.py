@@ -59,6 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         force = True
     else:
         so = SO
+    if os.environ.get("HM_BUILD_VARIANT"):
+        force = True
     if not force and not is_stale():
         return SO
     cmd = [
@@ -78,6 +80,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             cmd.insert(1, "-DHM_TC_EXPERIMENT=" + os.environ["HM_BUILD_EXPERIMENT"])
             so = os.path.join(HERE, f"libhm_matcher_exp{os.environ['HM_BUILD_EXPERIMENT']}.so")
             cmd[cmd.index("-o") + 1] = so
+    variant = os.environ.get("HM_BUILD_VARIANT")
+    if variant and not trace:   # experiment build: HM_BUILD_VARIANT=name HM_BUILD_FLAGS="-DX=1 -DY=2" -> libhm_matcher_<name>.so
+        so = os.path.join(HERE, f"libhm_matcher_{variant}.so")
+        cmd[cmd.index("-o") + 1] = so
+        for f in os.environ.get("HM_BUILD_FLAGS", "").split():
+            cmd.insert(1, f)
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -810,8 +810,9 @@ HM_API int hm_frame_put(hm_context* ctx, int slot, const uint8_t* desc_host, int
     FrameSlot& f = ctx->slots[slot];
     // the slot advertises rows only once their copy is enqueued: a failed allocation below leaves it empty
     f.n = 0;
-    f.has_points = false;
+    f.has_points = points_host != nullptr;      // an empty frame may still be "stored with positions"
     if (n == 0) return HM_OK;
+    f.has_points = false;
     const size_t bytes = slot_points_offset(n) + (size_t)n * 8;
     if (f.cap < bytes) {
         HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));        // kernels may still read the old buffer

@@ -9,6 +9,9 @@ v = os.environ.get("HM_TRACE_VARIANT", "f4")
 q = torch.from_numpy(synth.uniform(nq, 1)).cuda()
 t = torch.from_numpy(synth.uniform(nt, 2)).cuda()
 tp, qp = nat.prepare(t, variant=v), nat.prepare(q, variant=v)
+# sanity of an experiment build (timing-only builds with HM_TC_EXPERIMENT are wrong on purpose): tensor core == POPC
+cq, ct = q[:1000], t[:50000]
+same = torch.equal(nat.knn2_keys(cq, ct, variant=v), nat.knn2_keys(cq, ct, variant="popc"))
 for _ in range(3):
     nat.knn2_keys_prepared(qp, nq, tp, nt, variant=v)
 torch.cuda.synchronize()
@@ -22,4 +25,4 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / n
 tiles_per_sm = (nq + 255) // 256 * ((nt + 127) // 128) / nat.sm_count()
 print(f"{os.path.basename(nat.SO_PATH)} {v} {nq}x{nt}: {ms:.4f} ms, {nq * nt / ms / 1e6:.0f} Gpairs/s, "
-      f"{ms * 1e-3 * 1.965e9 / tiles_per_sm:.0f} cycles/tile at 1965 MHz")
+      f"{ms * 1e-3 * 1.965e9 / tiles_per_sm:.0f} cycles per 128 columns at 1965 MHz, results {'OK' if same else 'WRONG'}")

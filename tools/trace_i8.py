@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 # the trace stamps are compiled in only with -DHM_TC_TRACE=1: HM_BUILD_TRACE=1 python -m slam_experiments_b200.build
-os.environ["HM_MATCHER_SO"] = os.path.join(ROOT, "slam_experiments_b200", "libhm_matcher_trace.so")
+os.environ["HM_MATCHER_SO"] = os.environ.get("HM_TRACE_SO") or os.path.join(ROOT, "slam_experiments_b200", "libhm_matcher_trace.so")
 if not os.path.exists(os.environ["HM_MATCHER_SO"]):
     import subprocess
     subprocess.check_call([sys.executable, "-m", "slam_experiments_b200.build"], cwd=ROOT,
