@@ -45,7 +45,7 @@ extern "C" {
 #define HM_API __attribute__((visibility("default")))
 #endif
 
-#define HM_ABI_VERSION 2
+#define HM_ABI_VERSION 3
 #define HM_DESC_BYTES 32
 #define HM_DESC_BITS 256
 #define HM_NO_MATCH 0xFFFFFFFFFFFFFFFFull
@@ -123,6 +123,22 @@ HM_API int hm_knn2_batched(const uint8_t* query, int64_t nq, int64_t q_stride, i
                            const uint8_t* train, int64_t nt, int64_t t_stride, int64_t t_batch_stride,
                            int batch, uint64_t* out_keys,
                            int variant, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Resident database + packed query: the call a keyframe database makes per query batch.  `train_prepared` is an image
+ * written by hm_prepare(); `query` are plain descriptors (nq rows, q_stride bytes apart).  With HM_VARIANT_F4 the k-NN
+ * kernel expands the query rows itself (one launch per call); with HM_VARIANT_I8 the query is expanded into the tail of
+ * the workspace first.  Workspace: hm_resident_workspace_bytes(nq, nt, variant).  Same result as
+ * cv2.BFMatcher.knnMatch(query, train, k=2) (/root/reference/feature_matchers.py:39 for key[0]). */
+HM_API size_t hm_resident_workspace_bytes(int64_t nq, int64_t nt, int variant);
+HM_API int hm_knn2_resident(const uint8_t* query, int64_t nq, int64_t q_stride,
+                            const void* train_prepared, int64_t nt, uint64_t train_base, uint64_t* out_keys,
+                            int variant, void* workspace, size_t workspace_bytes, void* stream);
+/* the same with the cross-GPU exchange of hm_knn2_prepared_exchange folded into the kernel's last-CTA merge */
+HM_API int hm_knn2_resident_exchange(const uint8_t* query, int64_t nq, int64_t q_stride,
+                                     const void* train_prepared, int64_t nt, uint64_t train_base,
+                                     int world, int rank, void* const* peer_buffers_host, int64_t max_rows,
+                                     uint32_t epoch, uint64_t* out_keys, int variant, void* workspace,
+                                     size_t workspace_bytes, void* stream);
 
 /* ---- tensor-core operand preparation (resident keyframe database) ---------------------
  * `variant` selects the operand format: HM_VARIANT_I8, HM_VARIANT_F4, or HM_VARIANT_AUTO = the

@@ -34,6 +34,7 @@ EXPORTS = (
     "hm_version", "hm_last_error", "hm_profile_events", "hm_device_sm_count", "hm_select_variant", "hm_workspace_bytes",
     "hm_describe_launch",
     "hm_knn2", "hm_knn2_batched", "hm_default_tensor_variant", "hm_prepared_bytes", "hm_prepared_workspace_bytes", "hm_prepare", "hm_knn2_prepared", "hm_knn2_prepared_partials", "hm_knn2_prepared_exchange",
+    "hm_resident_workspace_bytes", "hm_knn2_resident", "hm_knn2_resident_exchange",
     "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused", "hm_gather_points", "hm_rasterize_mask",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host", "hm_frame_put", "hm_frame_match",
 )
@@ -74,6 +75,12 @@ def _declare(L):
     L.hm_prepare.argtypes = [vp, i64, i64, vp, ci, vp]
     L.hm_knn2_prepared.restype = ci
     L.hm_knn2_prepared.argtypes = [vp, i64, vp, i64, u64, vp, ci, vp, sz, vp]
+    L.hm_resident_workspace_bytes.restype = sz
+    L.hm_resident_workspace_bytes.argtypes = [i64, i64, ci]
+    L.hm_knn2_resident.restype = ci
+    L.hm_knn2_resident.argtypes = [vp, i64, i64, vp, i64, u64, vp, ci, vp, sz, vp]
+    L.hm_knn2_resident_exchange.restype = ci
+    L.hm_knn2_resident_exchange.argtypes = [vp, i64, i64, vp, i64, u64, ci, ci, vp, i64, c.c_uint32, vp, ci, vp, sz, vp]
     L.hm_merge_top2.restype = ci
     L.hm_merge_top2.argtypes = [vp, ci, i64, vp, vp]
     L.hm_exchange_bytes.restype = sz
@@ -291,6 +298,45 @@ def knn2_keys_prepared(query_prepared: torch.Tensor, nq: int, train_prepared: to
         ws = workspace(wsb, dev)
         check(L.hm_knn2_prepared(query_prepared.data_ptr(), nq, train_prepared.data_ptr(), nt, train_base,
                                  out.data_ptr(), v, ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "hm_knn2_prepared")
+    return out
+
+
+def knn2_keys_resident(query: torch.Tensor, train_prepared: torch.Tensor, nt: int, train_base: int = 0,
+                       out: Optional[torch.Tensor] = None, variant="auto") -> torch.Tensor:
+    """``hm_knn2_resident``: packed query descriptors against a resident prepared database -- one launch with the
+    ``f4`` core (the kernel expands the query rows itself)."""
+    _check_desc(query, "query")
+    dev = query.device
+    nq = query.shape[0]
+    if out is None:
+        out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
+    if nq == 0:
+        return out
+    v = tensor_variant(variant)
+    L = lib()
+    with on_device(dev):
+        ws = workspace(L.hm_resident_workspace_bytes(nq, nt, v), dev)
+        check(L.hm_knn2_resident(query.data_ptr(), nq, query.stride(0), train_prepared.data_ptr(), nt, train_base,
+                                 out.data_ptr(), v, ws.data_ptr(), ws.numel(), _stream_ptr(dev)), "hm_knn2_resident")
+    return out
+
+
+def knn2_resident_exchange(query: torch.Tensor, train_prepared: torch.Tensor, nt: int, train_base: int, world: int,
+                           rank: int, peer_ptrs, max_rows: int, epoch: int, out: Optional[torch.Tensor] = None,
+                           variant="auto") -> torch.Tensor:
+    """``hm_knn2_resident_exchange``: the same with the cross-GPU exchange inside the kernel's last-CTA merge."""
+    _check_desc(query, "query")
+    dev = query.device
+    nq = query.shape[0]
+    if out is None:
+        out = torch.empty((nq, 2), dtype=torch.int64, device=dev)
+    v = tensor_variant(variant)
+    L = lib()
+    with on_device(dev):
+        ws = workspace(L.hm_resident_workspace_bytes(nq, nt, v), dev)
+        check(L.hm_knn2_resident_exchange(query.data_ptr(), nq, query.stride(0), train_prepared.data_ptr(), nt, train_base,
+                                          world, rank, peer_ptrs, max_rows, epoch, out.data_ptr(), v, ws.data_ptr(),
+                                          ws.numel(), _stream_ptr(dev)), "hm_knn2_resident_exchange")
     return out
 
 

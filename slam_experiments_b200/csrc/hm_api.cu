@@ -367,6 +367,73 @@ HM_API int hm_knn2_prepared_exchange(const void* query_prepared, int64_t nq, con
                                    di.sm_count, v, static_cast<cudaStream_t>(stream), nullptr, nullptr, &x);
 }
 
+HM_API size_t hm_resident_workspace_bytes(int64_t nq, int64_t nt, int variant)
+{
+    DeviceInfo di;
+    int sm = 148;
+    if (device_info(&di) == HM_OK) sm = di.sm_count;
+    const int v = resolve_tensor_variant(variant);
+    if (v < 0) return 0;
+    if (nq <= 0 || nt <= 0) return 256;
+    return align_up(tc_resident_workspace_bytes(nq, nt, sm, v));
+}
+
+static int knn2_resident_common(const uint8_t* query, int64_t nq, int64_t q_stride, const void* train_prepared, int64_t nt,
+                                uint64_t train_base, uint64_t* out_keys, int variant, void* workspace,
+                                size_t workspace_bytes, void* stream, const ExchangeArgs* x, const char* who)
+{
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    const int v = resolve_tensor_variant(variant);
+    if (v < 0) return v;
+    if (nq < 0 || nt < 0) {
+        set_error("%s: negative row count", who);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    if (nq == 0) return HM_OK;
+    if (!out_keys) {
+        set_error("%s: out_keys is null", who);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    if ((rc = check_rows(query, nq, q_stride, "query")) != HM_OK) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (nt == 0 && !x) return fill_no_match(reinterpret_cast<unsigned long long*>(out_keys), nq * 2, st);
+    if (nt <= 0 || !train_prepared || (reinterpret_cast<uintptr_t>(train_prepared) & 15)) {
+        set_error("%s: the prepared database must be non-empty, non-null and 16-byte aligned", who);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    return launch_tc_knn2_resident(query, nq, q_stride, train_prepared, nt, train_base,
+                                   reinterpret_cast<unsigned long long*>(out_keys), workspace, workspace_bytes, di.sm_count,
+                                   v, st, x);
+}
+
+HM_API int hm_knn2_resident(const uint8_t* query, int64_t nq, int64_t q_stride, const void* train_prepared, int64_t nt,
+                            uint64_t train_base, uint64_t* out_keys, int variant, void* workspace,
+                            size_t workspace_bytes, void* stream)
+{
+    return knn2_resident_common(query, nq, q_stride, train_prepared, nt, train_base, out_keys, variant, workspace,
+                                workspace_bytes, stream, nullptr, "hm_knn2_resident");
+}
+
+HM_API int hm_knn2_resident_exchange(const uint8_t* query, int64_t nq, int64_t q_stride, const void* train_prepared,
+                                     int64_t nt, uint64_t train_base, int world, int rank,
+                                     void* const* peer_buffers_host, int64_t max_rows, uint32_t epoch, uint64_t* out_keys,
+                                     int variant, void* workspace, size_t workspace_bytes, void* stream)
+{
+    ExchangeArgs x;
+    DeviceInfo di;
+    int rc = device_info(&di);
+    if (rc != HM_OK) return rc;
+    if (nq <= 0 || nt <= 0) {
+        set_error("hm_knn2_resident_exchange: needs rows on both sides (every rank posts its flags)");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    if ((rc = fill_exchange_args(&x, world, rank, peer_buffers_host, max_rows, epoch, nq)) != HM_OK) return rc;
+    return knn2_resident_common(query, nq, q_stride, train_prepared, nt, train_base, out_keys, variant, workspace,
+                                workspace_bytes, stream, &x, "hm_knn2_resident_exchange");
+}
+
 HM_API int hm_merge_top2(const uint64_t* keys, int groups, int64_t rows, uint64_t* out_keys, void* stream)
 {
     DeviceInfo di;

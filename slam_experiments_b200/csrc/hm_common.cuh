@@ -36,6 +36,12 @@ struct KnnProblem {
     bool top1;                                // only the nearest neighbour is needed (second key may be HM_NO_MATCH)
 };
 
+// packed query descriptors handed to the tensor-core launcher (kind::mxf4 expands them inside the k-NN kernel)
+struct QueryBits {
+    const uint8_t* bits;
+    long long stride, batch_stride;
+};
+
 struct DeviceInfo {
     int device;
     int sm_count;
@@ -204,6 +210,10 @@ int launch_tc_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
                             size_t ws_bytes, int sm_count, int variant, cudaStream_t stream,
                             const unsigned long long** out_partials = nullptr, int* out_groups = nullptr,
                             const ExchangeArgs* exchange = nullptr);
+size_t tc_resident_workspace_bytes(long long nq, long long nt, int sm_count, int variant);
+int launch_tc_knn2_resident(const uint8_t* qbits, long long nq, long long q_stride, const void* tprep, long long nt,
+                            unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
+                            int sm_count, int variant, cudaStream_t stream, const ExchangeArgs* exchange = nullptr);
 int fill_exchange_args(ExchangeArgs* x, int world, int rank, void* const* peers, long long max_rows, unsigned epoch,
                        long long rows);
 size_t tc_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare, int variant);

@@ -205,6 +205,21 @@ __global__ void __launch_bounds__(256) hm_prepare_kernel(const PrepareParams P)
     dst[o] = v;
 }
 
+// 32 descriptor bits -> 32 e2m1 values (16 bytes): bit j -> nibble j, set = +1.0 (0x2), clear = -1.0 (0xA)
+__device__ __forceinline__ uint4 expand_bits_e2m1(unsigned bits32)
+{
+    unsigned w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const unsigned by = (bits32 >> (8 * i)) & 0xFF;
+        unsigned sgn = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sgn |= ((by >> j) & 1u) << (4 * j + 3);
+        w[i] = 0xAAAAAAAAu ^ sgn;
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // e2m1 image: one 128-byte slab per row, chunk c = descriptor bytes [4c, 4c+4)
 __global__ void __launch_bounds__(256) hm_prepare_f4_kernel(const PrepareParams P)
 {
@@ -221,17 +236,7 @@ __global__ void __launch_bounds__(256) hm_prepare_f4_kernel(const PrepareParams 
     uint4 v = make_uint4(0, 0, 0, 0);        // padding rows: +0.0 everywhere
     if (row < P.n) {
         const unsigned bits32 = *reinterpret_cast<const unsigned*>(P.bits + (long long)b * P.batch_stride + row * P.stride + c * 4);
-        unsigned w[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const unsigned by = (bits32 >> (8 * i)) & 0xFF;
-            // bit j -> bit 4j+3 (the e2m1 sign): set = +1.0 (0x2), clear = -1.0 (0xA)
-            unsigned s = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s |= ((by >> j) & 1u) << (4 * j + 3);
-            w[i] = 0xAAAAAAAAu ^ s;
-        }
-        v = make_uint4(w[0], w[1], w[2], w[3]);
+        v = expand_bits_e2m1(bits32);
     }
     uint4* dst = reinterpret_cast<uint4*>(P.out + (long long)b * P.padded_rows * HM_PREPARED_F4_ROW_BYTES);
     dst[o] = v;
@@ -241,6 +246,11 @@ __global__ void __launch_bounds__(256) hm_prepare_f4_kernel(const PrepareParams 
 // main kernel
 // ------------------------------------------------------------------------------------------
 struct TcParams {
+    // kind::mxf4 only: packed query descriptors.  When set, every CTA expands its 256 query rows into the A operand
+    // image in shared memory itself (8 KB of bits -> 32 KB of e2m1) and `qprep` is not read: no hm_prepare launch
+    // for the query side, one launch per k-NN call.
+    const uint8_t* qbits;
+    long long q_bits_stride, q_bits_batch_stride;
     const uint8_t* qprep;            // [batch][q_padded][row bytes]
     const uint8_t* tprep;            // [batch][t_padded][row bytes]
     long long nq, nt;
@@ -626,6 +636,22 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             ptx::tmem_st_32x32(taddr, ones);
             ptx::tmem_st_wait();
         }
+        if (P.qbits) {
+            // A operand from packed bits: the same swizzled image hm_prepare_f4_kernel writes, straight into shared
+            // memory (chunk position -> row and logical chunk as there); rows past nq are +0.0 like the padding
+            const uint8_t* qsrc = P.qbits + (long long)b * P.q_bits_batch_stride;
+            for (int o = threadIdx.x; o < kBlockM * 8; o += blockDim.x) {
+                const int blk = o >> 10, rem = o & 1023;
+                const int rr = (rem >> 3) & 7;
+                const int r = ((rem >> 6) << 3) | rr;
+                const int c = (rem & 7) ^ rr;
+                const long long qrow = (long long)qb * kBlockM + blk * kRowBlock + r;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (qrow < P.nq) v = expand_bits_e2m1(*reinterpret_cast<const unsigned*>(qsrc + qrow * P.q_bits_stride + c * 4));
+                reinterpret_cast<uint4*>(smem_a)[o] = v;
+            }
+            ptx::fence_proxy_async();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        }
         ptx::tc_fence_before();
         __syncthreads();
         ptx::tc_fence_after();
@@ -639,7 +665,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     if (warp == kProducerWarp) {
         // ===== producer: bulk async copies global -> shared =====
         if (lane == 0) {
-            if (has_a) {
+            if (has_a && !P.qbits) {
                 const uint8_t* qsrc = P.qprep + ((long long)b * P.q_padded + (long long)qb * kBlockM) * C::kRowBytes;
                 ptx::mbar_arrive_expect_tx(a_full_bar, kABytes);
                 ptx::bulk_g2s(smem_a, qsrc, kABytes, a_full_bar);       // two consecutive row blocks
@@ -683,7 +709,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         const uint32_t a_addr = ptx::smem_u32(smem_a) >> 4;       // descriptor start-address fields
         const uint32_t b_addr = ptx::smem_u32(smem_b) >> 4;
         const uint32_t tmem_sf = tmem_base + kScaleCol;
-        if (has_a) bounded_wait(a_full_bar, 0, P.error_flag);
+        if (has_a && !P.qbits) bounded_wait(a_full_bar, 0, P.error_flag);
         // The loop is unrolled over one period of the stage ring and of the unit rotation (kPeriod tiles), so that the
         // stage, the accumulator units, every barrier address, every descriptor offset and the unit parities are
         // compile-time constants: what is left per tile is the eight (sixteen) MMAs, three commits, the probes / waits
@@ -1148,7 +1174,7 @@ template <class C>
 int launch_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
                     unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
                     int sm_count, cudaStream_t stream, const unsigned long long** out_partials,
-                    int* out_groups, const ExchangeArgs* exchange, bool top1 = false)
+                    int* out_groups, const ExchangeArgs* exchange, bool top1 = false, const QueryBits* qbits = nullptr)
 {
     HM_CUDA_CHECK(ensure_smem_opt_in<C>());
     const TcPlan pl = plan_tc<C>(nq, nt, batch, sm_count);
@@ -1164,6 +1190,13 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
         return HM_ERR_WORKSPACE;
     }
     TcParams P{};
+    if (qbits && qbits->bits) {
+        if (!C::kScales) {
+            set_error("in-kernel query expansion exists for the kind::mxf4 core only");
+            return HM_ERR_UNSUPPORTED;
+        }
+        P.qbits = qbits->bits; P.q_bits_stride = qbits->stride; P.q_bits_batch_stride = qbits->batch_stride;
+    }
     P.qprep = static_cast<const uint8_t*>(qprep);
     P.tprep = static_cast<const uint8_t*>(tprep);
     P.nq = nq; P.nt = nt;
@@ -1319,12 +1352,18 @@ int launch_knn2_of(const KnnProblem& p, unsigned long long* out, void* ws, size_
     const size_t head = workspace_bytes_of<C>(p.nq, p.nt, p.batch, sm_count, false);
     uint8_t* qprep = static_cast<uint8_t*>(ws) + head;
     uint8_t* tprep = qprep + (size_t)padded_rows<C>(p.nq) * C::kRowBytes * p.batch;
-    int rc = launch_prepare_of<C>(p.q, p.nq, p.q_stride, p.q_batch_stride, p.batch, qprep, stream);
-    if (rc != HM_OK) return rc;
+    int rc = HM_OK;
+    QueryBits qb{};
+    if (C::kScales) {           // kind::mxf4: the k-NN kernel expands the query rows itself
+        qb.bits = p.q; qb.stride = p.q_stride; qb.batch_stride = p.q_batch_stride;
+    } else {
+        rc = launch_prepare_of<C>(p.q, p.nq, p.q_stride, p.q_batch_stride, p.batch, qprep, stream);
+        if (rc != HM_OK) return rc;
+    }
     rc = launch_prepare_of<C>(p.t, p.nt, p.t_stride, p.t_batch_stride, p.batch, tprep, stream);
     if (rc != HM_OK) return rc;
     return launch_prepared<C>(qprep, p.nq, tprep, p.nt, p.batch, p.train_base, out, ws, head, sm_count, stream, nullptr,
-                              nullptr, nullptr, p.top1);
+                              nullptr, nullptr, p.top1, &qb);
 }
 
 }  // namespace
@@ -1358,6 +1397,37 @@ int launch_tc_knn2_prepared(const void* qprep, long long nq, const void* tprep, 
                                          out_partials, out_groups, exchange)
                : launch_prepared<CoreI8>(qprep, nq, tprep, nt, batch, train_base, out, ws, ws_bytes, sm_count, stream,
                                          out_partials, out_groups, exchange);
+}
+
+// resident database, query as packed bits: kind::mxf4 expands the query inside the k-NN kernel; kind::i8 expands it into
+// the tail of the workspace first (ws_bytes must be tc_resident_workspace_bytes)
+size_t tc_resident_workspace_bytes(long long nq, long long nt, int sm_count, int variant)
+{
+    size_t b = (tc_workspace_bytes(nq, nt, 1, sm_count, false, variant) + 1023) & ~(size_t)1023;
+    if (variant != HM_VARIANT_F4) b += prepared_bytes(nq, variant);
+    return b;
+}
+
+int launch_tc_knn2_resident(const uint8_t* qbits, long long nq, long long q_stride, const void* tprep, long long nt,
+                            unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
+                            int sm_count, int variant, cudaStream_t stream, const ExchangeArgs* exchange)
+{
+    const size_t need = tc_resident_workspace_bytes(nq, nt, sm_count, variant);
+    if (!ws || ws_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return HM_ERR_WORKSPACE;
+    }
+    if (variant == HM_VARIANT_F4) {
+        QueryBits qb{qbits, q_stride, 0};
+        return launch_prepared<CoreF4>(nullptr, nq, tprep, nt, 1, train_base, out, ws, ws_bytes, sm_count, stream, nullptr,
+                                       nullptr, exchange, false, &qb);
+    }
+    const size_t head = (tc_workspace_bytes(nq, nt, 1, sm_count, false, variant) + 1023) & ~(size_t)1023;
+    uint8_t* qprep = static_cast<uint8_t*>(ws) + head;
+    const int rc = launch_prepare_of<CoreI8>(qbits, nq, q_stride, 0, 1, qprep, stream);
+    if (rc != HM_OK) return rc;
+    return launch_prepared<CoreI8>(qprep, nq, tprep, nt, 1, train_base, out, ws, head, sm_count, stream, nullptr, nullptr,
+                                   exchange);
 }
 
 // "kernel grid=(x,y,z) cluster=c" of the launch the given shape would get (introspection for bench / docs)

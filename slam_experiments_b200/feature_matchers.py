@@ -76,6 +76,10 @@ def _load_fast_builder():
         rows = _hmfast.dmatch_build(DMatch, np.array([7, 1], np.int32), np.array([9, 2], np.int32),
                                     np.array([12.0, 256.0], np.float32), np.array([4, 5], np.int32), 0, 2)
         ok = ok and isinstance(probe[0], DMatch) and [m.imgIdx for m in rows[0]] == [4, 5]
+        pre = _hmfast.dmatch_alloc(DMatch, 2, 2)
+        _hmfast.dmatch_fill(pre, np.array([7, 1], np.int32), np.array([9, 2], np.int32),
+                            np.array([12.0, 256.0], np.float32), np.array([4, 5], np.int32), 0, 2)
+        ok = ok and [(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in pre[0]] == [(7, 9, 4, 12.0), (1, 2, 5, 256.0)]
         return _hmfast.dmatch_build if ok else None
     except Exception:
         return None
@@ -107,6 +111,29 @@ def _build_dmatches(q, t, d, img=0, rows: int = 0):
     if rows:
         return tuple(tuple(out[i:i + rows]) for i in range(0, len(out), rows))
     return out
+
+
+def _prealloc_dmatches(n: int, rows: int = 0):
+    """Containers + DMatch objects for ``n`` results, fields still zero: object allocation is the expensive part of the
+    result list, and for knnMatch its size (``nq * k``) is known before the kernels finish -- so it runs while they do.
+    Returns None when the C helper is unavailable (the caller then builds the list afterwards)."""
+    if _fast_build is None or n <= 0:
+        return None
+    try:
+        from . import _hmfast
+        return _hmfast.dmatch_alloc(DMatch, int(n), int(rows))
+    except Exception:
+        return None
+
+
+def _fill_dmatches(container, q, t, d, img=0, rows: int = 0):
+    from . import _hmfast
+    q = np.ascontiguousarray(q, dtype=np.int32)
+    t = np.ascontiguousarray(t, dtype=np.int32)
+    d = np.ascontiguousarray(d, dtype=np.float32)
+    img_arr = None if isinstance(img, (int, np.integer)) else np.ascontiguousarray(img, dtype=np.int32)
+    _hmfast.dmatch_fill(container, q, t, d, img_arr, 0 if img_arr is not None else int(img), rows)
+    return container
 
 
 class _Staging:

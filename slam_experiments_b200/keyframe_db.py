@@ -22,7 +22,7 @@ import numpy as np
 import torch
 
 from . import _native as nat
-from .feature_matchers import MatcherError, _Staging, _build_dmatches
+from .feature_matchers import MatcherError, _Staging, _build_dmatches, _fill_dmatches, _prealloc_dmatches
 
 
 def shard_ranges(sizes: Sequence[int], world_size: int) -> List[Tuple[int, int, int, int]]:
@@ -119,17 +119,18 @@ class NativeOps:
 
     def local_knn2(self, query: torch.Tensor, shard, train_base: int) -> torch.Tensor:
         if shard["prepared"] is not None and query.shape[0] > 0:
-            qprep = nat.prepare(query, variant=shard["tc"])
-            return nat.knn2_keys_prepared(qprep, query.shape[0], shard["prepared"], shard["nt"], train_base,
-                                          variant=shard["tc"])
+            # resident prepared database, packed query: one launch with the f4 core (query expanded in-kernel)
+            return nat.knn2_keys_resident(query, shard["prepared"], shard["nt"], train_base, variant=shard["tc"])
         return nat.knn2_keys(query, shard["bits"], train_base=train_base, variant=self.variant)
 
     def launches_per_step(self, shard, world: int, exchange_mode: str) -> int:
         """Kernels of THIS library launched per ``knn2_keys_device`` call (bench.py's ``gpu_launches``; the ncu launch
-        lists under profiles/ are the evidence): query expansion + k-NN for a prepared shard (the split merge and the
-        fused exchange run inside the k-NN kernel), k-NN (+ split merge) for packed bits, + hm_exchange_merge or
-        hm_merge_top2 when the exchange is a launch of its own."""
-        n = 2 if shard["prepared"] is not None else 2
+        lists under profiles/ are the evidence): the k-NN kernel for a prepared shard (query expansion, split merge and
+        the fused exchange run inside it; the i8 core expands the query in a launch of its own), k-NN (+ split merge) for
+        packed bits, + hm_exchange_merge or hm_merge_top2 when the exchange is a launch of its own."""
+        # f4 resident shard: ONE launch (the kernel expands the query itself); i8: query expansion + k-NN;
+        # packed bits: k-NN + split merge
+        n = (1 if shard["tc"] == nat.VARIANT_F4 else 2) if shard["prepared"] is not None else 2
         if world > 1 and (exchange_mode != "fused" or shard["prepared"] is None or self.exchange_kernel != "in_knn"):
             n += 1
         return n
@@ -184,11 +185,11 @@ class NativeOps:
             return self.merge(self.all_gather(self.local_knn2(query, shard, train_base), group))
         if shard["prepared"] is None:
             return self.gather_merge(self.local_knn2(query, shard, train_base), group)
-        qprep = nat.prepare(query, variant=shard["tc"])
         x["epoch"] += 1
         if self.exchange_kernel == "in_knn":
-            return nat.knn2_prepared_exchange(qprep, nq, shard["prepared"], shard["nt"], train_base, x["world"],
-                                              x["rank"], x["ptrs"], x["max_rows"], x["epoch"], variant=shard["tc"])
+            return nat.knn2_resident_exchange(query, shard["prepared"], shard["nt"], train_base, x["world"], x["rank"],
+                                              x["ptrs"], x["max_rows"], x["epoch"], variant=shard["tc"])
+        qprep = nat.prepare(query, variant=shard["tc"])
         ptr, groups = nat.knn2_partials_prepared(qprep, nq, shard["prepared"], shard["nt"], train_base,
                                                  variant=shard["tc"])
         return nat.exchange_merge(ptr, x["world"], x["rank"], x["ptrs"], x["max_rows"], x["epoch"], rows=nq,
@@ -286,7 +287,7 @@ class ShardedKeyframeDatabase:
         return self.ops.merge(gathered)
 
     # ---- host-level API -----------------------------------------------------------------------
-    def knn_tensors(self, query: np.ndarray, k: int = 2):
+    def knn_tensors(self, query: np.ndarray, k: int = 2, while_running=None):
         """``(imgIdx, trainIdx, distance)`` each ``[Nq, k']``: cv2's collection result as arrays."""
         if k not in (1, 2):
             raise MatcherError("only k in {1, 2} is supported on the B200 path")
@@ -296,7 +297,10 @@ class ShardedKeyframeDatabase:
             return e, e.copy(), e.copy()
         if q.dtype != np.uint8 or q.ndim != 2 or q.shape[1] != nat.DESC_BYTES:
             raise MatcherError("query: expected uint8 [N, 32] descriptors")
-        keys = self.ops.to_host(self.knn2_keys_device(self.ops.upload(q)))
+        keys_dev = self.knn2_keys_device(self.ops.upload(q))      # enqueued, not finished
+        if while_running is not None:
+            while_running()                                       # host work that overlaps the kernels
+        keys = self.ops.to_host(keys_dev)
         gidx, dist, valid = nat.split_keys(keys)
         kk = min(k, int(valid[0].sum()))
         gidx, dist = gidx[:, :kk], dist[:, :kk]
@@ -305,9 +309,19 @@ class ShardedKeyframeDatabase:
 
     def knnMatch(self, queryDescriptors, k: int = 2) -> tuple:
         """cv2 ``bf.knnMatch(query, k)`` over the whole (sharded) collection."""
-        img, local, dist = self.knn_tensors(queryDescriptors, k)
+        # the result has nq * min(k, rows in the collection) entries whatever the distances turn out to be, so the DMatch
+        # objects are allocated while the kernels run and only filled in afterwards
+        q = np.asarray(queryDescriptors)
+        kk_known = min(k, int(self.starts[-1])) if k in (1, 2) else 0
+        pre = []
+        if q.ndim == 2 and kk_known > 0:
+            img, local, dist = self.knn_tensors(q, k, while_running=lambda: pre.append(_prealloc_dmatches(q.shape[0] * kk_known, kk_known)))
+        else:
+            img, local, dist = self.knn_tensors(queryDescriptors, k)
         nq, kk = img.shape
         if kk == 0:
             return tuple(() for _ in range(nq))
         qi = np.repeat(np.arange(nq, dtype=np.int32), kk)
+        if pre and pre[0] is not None and kk == kk_known:
+            return _fill_dmatches(pre[0], qi, local.reshape(-1), dist.reshape(-1), img.reshape(-1), rows=kk)
         return _build_dmatches(qi, local.reshape(-1), dist.reshape(-1), img.reshape(-1), rows=kk)

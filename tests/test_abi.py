@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_version_and_sizing(lib):
-    assert lib.hm_version() == 2
+    assert lib.hm_version() == 3
     I8, F4 = nat.VARIANT_I8, nat.VARIANT_F4
     assert lib.hm_prepared_bytes(0, I8) == 0
     assert lib.hm_prepared_bytes(1, I8) == 256 * 256        # padded to whole 256-row tiles
@@ -52,6 +52,9 @@ def test_version_and_sizing(lib):
     for v in (I8, F4):
         assert lib.hm_workspace_bytes(2000, 8192000, 1, v) >= lib.hm_prepared_bytes(8192000, v)
         assert lib.hm_prepared_workspace_bytes(2000, 8192000, v) > 0
+        assert lib.hm_resident_workspace_bytes(2000, 8192000, v) >= lib.hm_prepared_workspace_bytes(2000, 8192000, v)
+    # the i8 core expands the query into the workspace, the f4 core inside the k-NN kernel
+    assert lib.hm_resident_workspace_bytes(2000, 8192000, I8) >= lib.hm_resident_workspace_bytes(2000, 8192000, F4) + lib.hm_prepared_bytes(2000, I8) - 4096
     assert lib.hm_select_variant(200, 200, 1) == nat.VARIANT_POPC
     assert lib.hm_select_variant(16384, 16384, 1) == tc
 

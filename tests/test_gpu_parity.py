@@ -456,3 +456,26 @@ def test_back_to_back_uploads_do_not_alias_staging():
     kb = bf.knn_keys_device(qb, t)
     assert np.array_equal(ka.cpu().numpy().view(np.uint64), co.knn2_keys(qa, t))
     assert np.array_equal(kb.cpu().numpy().view(np.uint64), co.knn2_keys(qb, t))
+
+
+@pytest.mark.parametrize("variant", ("i8", "f4"))
+def test_resident_database_packed_query(variant):
+    """hm_knn2_resident: packed query rows against a prepared database.  The f4 core expands the query inside the
+    k-NN kernel (every CTA writes its own A operand image): ragged query counts, padding rows inside the last
+    256-row block, strided query views, a train_base."""
+    rng = np.random.default_rng(31)
+    t = rng.integers(0, 256, (70001, 32), dtype=np.uint8)
+    tp = nat.prepare(dev(t), variant=variant)
+    for nq in (1, 127, 256, 257, 700, 2000, 4097):
+        q = rng.integers(0, 256, (nq, 32), dtype=np.uint8)
+        q[: min(nq, 40)] = t[rng.choice(t.shape[0], min(nq, 40), replace=False)]         # exact matches: distance 0
+        got = nat.knn2_keys_resident(dev(q), tp, t.shape[0], train_base=5, variant=variant)
+        assert np.array_equal(got.cpu().numpy().view(np.uint64), co.knn2_keys(q, t, train_base=5)), nq
+    wide = rng.integers(0, 256, (900, 64), dtype=np.uint8)
+    got = nat.knn2_keys_resident(torch.from_numpy(wide).cuda()[:, 32:], tp, t.shape[0], variant=variant)
+    assert np.array_equal(got.cpu().numpy().view(np.uint64), co.knn2_keys(wide[:, 32:], t))
+    # tie-heavy low-entropy rows through the same path
+    t2 = rng.integers(0, 3, (30000, 32), dtype=np.uint8)
+    q2 = rng.integers(0, 3, (513, 32), dtype=np.uint8)
+    got = nat.knn2_keys_resident(dev(q2), nat.prepare(dev(t2), variant=variant), t2.shape[0], variant=variant)
+    assert np.array_equal(got.cpu().numpy().view(np.uint64), co.knn2_keys(q2, t2))

@@ -124,3 +124,35 @@ def test_locate_rows_equals_searchsorted():
         img, loc = nat.locate_rows(starts, g)
         e = np.searchsorted(starts, g, side="right") - 1
         assert img.dtype == np.int32 and np.array_equal(img, e) and np.array_equal(loc, g - starts[e]), sizes[:4]
+
+
+def test_dmatch_builders_agree(monkeypatch):
+    """cv2.DMatch objects from the C helper (direct field writes through an assumed object layout, probed at import),
+    from its two-phase twin (allocate while the kernels run, fill afterwards) and from the pure-Python fallback
+    (the type's own constructor) are identical, for the flat (match) and the row (knnMatch) shapes."""
+    cv2 = pytest.importorskip("cv2")
+    from slam_experiments_b200 import feature_matchers as fm
+    rng = np.random.default_rng(4)
+    n = 600
+    q = np.repeat(np.arange(n // 2, dtype=np.int32), 2)
+    t = rng.integers(0, 1 << 18, n).astype(np.int32)
+    d = rng.integers(0, 257, n).astype(np.float32)
+    img = rng.integers(0, 8191, n).astype(np.int32)
+
+    def rows_of(out, rows):
+        flat = [m for r in out for m in r] if rows else list(out)
+        assert all(type(m) is cv2.DMatch for m in flat)
+        return [(m.queryIdx, m.trainIdx, m.imgIdx, m.distance) for m in flat], type(out), (type(out[0]) if rows else None)
+
+    for rows in (0, 2):
+        for im in (0, 3, img):
+            fast = fm._build_dmatches(q, t, d, im, rows=rows)
+            with monkeypatch.context() as mp:
+                mp.setattr(fm, "_fast_build", None)
+                slow = fm._build_dmatches(q, t, d, im, rows=rows)
+            assert rows_of(fast, rows) == rows_of(slow, rows)
+            if fm._fast_build is not None:
+                pre = fm._prealloc_dmatches(n, rows)
+                assert pre is not None
+                assert rows_of(fm._fill_dmatches(pre, q, t, d, im, rows=rows), rows) == rows_of(slow, rows)
+    assert fm._fast_build is not None, "the C helper should load in this image (falls back silently elsewhere)"

@@ -6,8 +6,11 @@ import torch
 from slam_experiments_b200 import _native as nat, synth
 nq, nt = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (2000, 8192000)
 v = os.environ.get("HM_TRACE_VARIANT", "f4")
-q = torch.from_numpy(synth.uniform(nq, 1)).cuda()
-t = torch.from_numpy(synth.uniform(nt, 2)).cuda()
+t_host = synth.uniform(nt, 2)
+# HM_TP_DIST=M: matchable queries (60 % noisy copies of train rows), the distribution bench.py's C4 line uses
+q_host = synth.matchable_queries(t_host, nq, 3) if os.environ.get("HM_TP_DIST") == "M" else synth.uniform(nq, 1)
+q = torch.from_numpy(q_host).cuda()
+t = torch.from_numpy(t_host).cuda()
 tp, qp = nat.prepare(t, variant=v), nat.prepare(q, variant=v)
 # sanity of an experiment build (timing-only builds with HM_TC_EXPERIMENT are wrong on purpose): tensor core == POPC
 cq, ct = q[:1000], t[:50000]
@@ -16,7 +19,7 @@ for _ in range(3):
     nat.knn2_keys_prepared(qp, nq, tp, nt, variant=v)
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-n = 20
+n = int(os.environ.get("HM_TP_ITERS", "20"))
 e0.record()
 for _ in range(n):
     nat.knn2_keys_prepared(qp, nq, tp, nt, variant=v)
