@@ -244,6 +244,17 @@ HM_API void hm_context_destroy(hm_context* ctx);
 HM_API int hm_knn2_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
                         const uint8_t* train_host, int64_t nt, uint64_t* out_keys_host, int variant);
 
+/* Host-buffer query of a resident prepared database (the keyframe-database step, numpy in / keys out): pinned staging
+ * and H2D of the packed query, hm_knn2_resident (world <= 1) or hm_knn2_resident_exchange, D2H of the keys, all on the
+ * context's stream.  _begin only enqueues -- the caller may allocate its result objects while the kernel runs -- and
+ * _end synchronises and copies the nq x 2 keys out.  One query in flight per context.  The database must have been
+ * prepared before the call (synchronise the stream that ran hm_prepare). */
+HM_API int hm_resident_query_begin(hm_context* ctx, const uint8_t* query_host, int64_t nq, int64_t q_stride,
+                                   const void* train_prepared, int64_t nt, uint64_t train_base, int variant,
+                                   int world, int rank, void* const* peer_buffers_host, int64_t max_rows,
+                                   uint32_t epoch);
+HM_API int hm_resident_query_end(hm_context* ctx, int64_t nq, uint64_t* out_keys_host);
+
 /* numpy-in / numpy-out twin of hm_match_fused (batch = 1): H2D of both descriptor sets through
  * pinned staging, k-NN (+ swapped pass with HM_FLAG_MUTUAL), filter, D2H, one synchronisation.
  * out_q/out_t/out_d_host[nq] int32, *out_count_host = number of matches (ordered by queryIdx).

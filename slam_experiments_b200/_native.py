@@ -37,6 +37,7 @@ EXPORTS = (
     "hm_resident_workspace_bytes", "hm_knn2_resident", "hm_knn2_resident_exchange",
     "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused", "hm_gather_points", "hm_rasterize_mask",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host", "hm_frame_put", "hm_frame_match",
+    "hm_resident_query_begin", "hm_resident_query_end",
 )
 
 
@@ -104,6 +105,10 @@ def _declare(L):
     L.hm_context_create.argtypes = [c.POINTER(vp)]
     L.hm_context_destroy.restype = None
     L.hm_context_destroy.argtypes = [vp]
+    L.hm_resident_query_begin.restype = ci
+    L.hm_resident_query_begin.argtypes = [vp, vp, i64, i64, vp, i64, u64, ci, ci, ci, vp, i64, c.c_uint32]
+    L.hm_resident_query_end.restype = ci
+    L.hm_resident_query_end.argtypes = [vp, i64, vp]
     L.hm_knn2_host.restype = ci
     L.hm_knn2_host.argtypes = [vp, vp, i64, vp, i64, vp, ci]
     L.hm_frame_put.restype = ci
@@ -618,6 +623,23 @@ class HostContext:
                                   out[2].ctypes.data, ctypes.byref(cnt)), "hm_match_host")
         n = cnt.value
         return out[0, :n], out[1, :n], out[2, :n]
+
+    # ---- resident prepared database queried from host memory (hm_resident_query_begin / _end) ----
+    def resident_query_begin(self, query: np.ndarray, train_prepared: torch.Tensor, nt: int, train_base: int = 0,
+                             variant="auto", world: int = 1, rank: int = 0, peer_ptrs=None, max_rows: int = 0,
+                             epoch: int = 0) -> int:
+        q = query
+        if q.strides[1] != 1 or q.strides[0] < DESC_BYTES:
+            q = np.ascontiguousarray(q)
+        check(lib().hm_resident_query_begin(self._h, q.ctypes.data, q.shape[0], q.strides[0], train_prepared.data_ptr(), nt,
+                                            train_base, tensor_variant(variant), world, rank, peer_ptrs, max_rows, epoch),
+              "hm_resident_query_begin")
+        return q.shape[0]
+
+    def resident_query_end(self, nq: int) -> np.ndarray:
+        out = np.empty((nq, 2), dtype=np.uint64)
+        check(lib().hm_resident_query_end(self._h, nq, out.ctypes.data), "hm_resident_query_end")
+        return out
 
     # ---- resident frames (hm_frame_put / hm_frame_match) ----
     FRAME_SLOTS = 16

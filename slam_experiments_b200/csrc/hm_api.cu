@@ -860,6 +860,49 @@ HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
     return HM_OK;
 }
 
+// ---- resident keyframe database queried from host memory (the e2e path of the C4 workload) --------------------
+// One query batch against a prepared database that stays on the device: pinned staging + H2D of the packed query,
+// hm_knn2_resident (or its cross-GPU twin), D2H of the keys.  Split in two calls so that the host can do useful work
+// (allocating the result objects) while the kernel runs: _begin enqueues, _end synchronises and copies out.
+HM_API int hm_resident_query_begin(hm_context* ctx, const uint8_t* query_host, int64_t nq, int64_t q_stride,
+                                   const void* train_prepared, int64_t nt, uint64_t train_base, int variant, int world,
+                                   int rank, void* const* peer_buffers_host, int64_t max_rows, uint32_t epoch)
+{
+    if (!ctx || nq <= 0 || nt <= 0 || !query_host || !train_prepared || q_stride < HM_DESC_BYTES) {
+        set_error("hm_resident_query_begin: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    const size_t qb = align_up((size_t)nq * HM_DESC_BYTES, 1024), kb = align_up((size_t)nq * 16, 1024);
+    const size_t wsb = align_up(hm_resident_workspace_bytes(nq, nt, variant), 1024);
+    int rc = ctx_reserve(ctx, qb + kb + wsb, qb + kb);
+    if (rc != HM_OK) return rc;
+    uint8_t *dq = ctx->d_buf, *dk = dq + qb, *dw = dk + kb;
+    uint8_t *hq = ctx->h_buf, *hk = hq + qb;
+    copy_rows(hq, query_host, nq, q_stride);
+    HM_CUDA_CHECK(cudaMemcpyAsync(dq, hq, (size_t)nq * HM_DESC_BYTES, cudaMemcpyHostToDevice, ctx->stream));
+    if (world > 1)
+        rc = hm_knn2_resident_exchange(dq, nq, HM_DESC_BYTES, train_prepared, nt, train_base, world, rank, peer_buffers_host,
+                                       max_rows, epoch, reinterpret_cast<uint64_t*>(dk), variant, dw, wsb, ctx->stream);
+    else
+        rc = hm_knn2_resident(dq, nq, HM_DESC_BYTES, train_prepared, nt, train_base, reinterpret_cast<uint64_t*>(dk), variant,
+                              dw, wsb, ctx->stream);
+    if (rc != HM_OK) return rc;
+    HM_CUDA_CHECK(cudaMemcpyAsync(hk, dk, (size_t)nq * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    return HM_OK;
+}
+
+HM_API int hm_resident_query_end(hm_context* ctx, int64_t nq, uint64_t* out_keys_host)
+{
+    if (!ctx || nq <= 0 || !out_keys_host || !ctx->h_buf) {
+        set_error("hm_resident_query_end: bad arguments");
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    const size_t qb = align_up((size_t)nq * HM_DESC_BYTES, 1024);
+    memcpy(out_keys_host, ctx->h_buf + qb, (size_t)nq * 16);
+    return HM_OK;
+}
+
 // ---- resident frames behind the context (SURVEY.md 8f ranks 1 + 2) --------------------------------------
 // The reference repacks and hands BOTH frames to the matcher on every call (frontend.py:181-187,
 // primitives.py:200-205).  Here a frame is uploaded once into a slot -- descriptors and, optionally, its

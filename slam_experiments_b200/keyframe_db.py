@@ -202,6 +202,35 @@ class NativeOps:
             return nat.exchange_merge(local.contiguous(), x["world"], x["rank"], x["ptrs"], x["max_rows"], x["epoch"])
         return self.merge(self.all_gather(local, group))
 
+    # ---- host-buffer query of the resident shard through the C context (one C call to enqueue, one to finish) ----
+    def host_query_begin(self, query: np.ndarray, shard, train_base: int, world: int):
+        """Enqueue query upload + k-NN (+ fused exchange) + key download on the context's stream; returns a token for
+        :meth:`host_query_end`, or None when this path does not apply (no prepared shard, exchange over NCCL, a query
+        larger than the symmetric buffer): the caller then takes the torch-level path."""
+        x = getattr(self, "_xch", None)
+        nq = query.shape[0]
+        if shard["prepared"] is None or nq == 0 or query.dtype != np.uint8:
+            return None
+        if world > 1 and (x is None or self.exchange_kernel != "in_knn" or nq > x["max_rows"]):
+            return None
+        if getattr(self, "_hctx", None) is None:
+            with nat.on_device(self.device):
+                torch.cuda.synchronize(self.device)         # the shard's prepared image was written on torch's stream
+                self._hctx = nat.HostContext()
+        if shard.get("_host_epoch") != id(shard["prepared"]) or shard.get("_host_nt") != shard["nt"]:
+            torch.cuda.synchronize(self.device)             # the shard grew / moved since the last query
+            shard["_host_epoch"], shard["_host_nt"] = id(shard["prepared"]), shard["nt"]
+        with nat.on_device(self.device):
+            if world > 1:
+                x["epoch"] += 1
+                return self._hctx.resident_query_begin(query, shard["prepared"], shard["nt"], train_base, shard["tc"],
+                                                       x["world"], x["rank"], x["ptrs"], x["max_rows"], x["epoch"])
+            return self._hctx.resident_query_begin(query, shard["prepared"], shard["nt"], train_base, shard["tc"])
+
+    def host_query_end(self, token) -> np.ndarray:
+        with nat.on_device(self.device):
+            return self._hctx.resident_query_end(token).view(np.int64)
+
     def to_host(self, keys: torch.Tensor) -> np.ndarray:
         with nat.on_device(self.device):
             return self._staging.to_host("keys", keys)
@@ -297,10 +326,14 @@ class ShardedKeyframeDatabase:
             return e, e.copy(), e.copy()
         if q.dtype != np.uint8 or q.ndim != 2 or q.shape[1] != nat.DESC_BYTES:
             raise MatcherError("query: expected uint8 [N, 32] descriptors")
-        keys_dev = self.knn2_keys_device(self.ops.upload(q))      # enqueued, not finished
+        token = None
+        if hasattr(self.ops, "host_query_begin") and (self.world_size == 1 or self.exchange_mode == "fused"):
+            token = self.ops.host_query_begin(q, self.shard, self.row_lo, self.world_size)
+        if token is None:
+            keys_dev = self.knn2_keys_device(self.ops.upload(q))  # enqueued, not finished
         if while_running is not None:
             while_running()                                       # host work that overlaps the kernels
-        keys = self.ops.to_host(keys_dev)
+        keys = self.ops.host_query_end(token) if token is not None else self.ops.to_host(keys_dev)
         gidx, dist, valid = nat.split_keys(keys)
         kk = min(k, int(valid[0].sum()))
         gidx, dist = gidx[:, :kk], dist[:, :kk]

@@ -12,8 +12,15 @@ from oracle import c_oracle
 
 
 def check(db, q, cat, rank, what):
+    """device-level call (torch tensors) and host-level call (numpy in, the C host context where it applies)"""
+    from slam_experiments_b200 import _native as nat
+    expect = c_oracle.knn2_keys(q, cat)
     keys = db.knn2_keys_device(torch.from_numpy(q).cuda()).cpu().numpy().view(np.uint64)
-    good = np.array_equal(keys, c_oracle.knn2_keys(q, cat))
+    good = np.array_equal(keys, expect)
+    img, loc, d = db.knn_tensors(q, 2)
+    gidx, gdist, _ = nat.split_keys(expect)
+    eimg, eloc = nat.locate_rows(db.starts, gidx)
+    good &= np.array_equal(img, eimg) and np.array_equal(loc, eloc) and np.array_equal(d, gdist)
     if not good:
         print(f"rank {rank} {what} nq {q.shape[0]}: MISMATCH", flush=True)
     return good
