@@ -138,6 +138,11 @@ size_t knn_workspace(long long nq, long long nt, int batch, int variant, int sm_
     return align_up(a > b ? a : b);
 }
 
+// candidate selection of the mutual check: [count: batch ints, padded | slot_of: batch x nt ints] (zeroed per call)
+// followed by [list: batch x nt ints]
+inline size_t select_zeroed_bytes(long long nt, int batch) { return align_up((size_t)batch * 4) + align_up((size_t)batch * nt * 4); }
+inline size_t select_bytes(long long nt, int batch) { return select_zeroed_bytes(nt, batch) + align_up((size_t)batch * nt * 4); }
+
 __global__ void hm_fill_keys_kernel(unsigned long long* p, long long n)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -236,7 +241,7 @@ HM_API size_t hm_workspace_bytes(int64_t nq, int64_t nt, int batch, int variant)
     const size_t bwd = align_up((size_t)batch * nt * 16);
     const size_t a = knn_workspace(nq, nt, batch, variant, sm);
     const size_t b = knn_workspace(nt, nq, batch, variant, sm);
-    return fwd + bwd + (a > b ? a : b) + 256;
+    return fwd + bwd + select_bytes(nt, batch) + (a > b ? a : b) + 256;
 }
 
 HM_API int hm_knn2(const uint8_t* query, int64_t nq, int64_t q_stride, const uint8_t* train, int64_t nt,
@@ -542,8 +547,10 @@ HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, in
     unsigned long long* fwd = out_keys ? reinterpret_cast<unsigned long long*>(out_keys)
                                        : reinterpret_cast<unsigned long long*>(ws);
     unsigned long long* bwd = reinterpret_cast<unsigned long long*>(ws + fwd_bytes);
-    uint8_t* knn_ws = ws + fwd_bytes + bwd_bytes;
-    const size_t knn_ws_bytes = workspace_bytes - fwd_bytes - bwd_bytes;
+    uint8_t* sel_ws = ws + fwd_bytes + bwd_bytes;
+    const size_t sel_bytes = select_bytes(nt, batch);
+    uint8_t* knn_ws = sel_ws + sel_bytes;
+    const size_t knn_ws_bytes = workspace_bytes - fwd_bytes - bwd_bytes - sel_bytes;
 
     KnnProblem p{};
     p.q = query; p.t = train; p.nq = nq; p.nt = nt; p.q_stride = q_stride; p.t_stride = t_stride;
@@ -551,8 +558,34 @@ HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, in
     // cv2.BFMatcher.match() -- the reference's own call (feature_matchers.py:39) -- is k = 1: without the ratio
     // test nobody reads the second neighbour
     p.top1 = !(flags & HM_FLAG_RATIO) && !out_keys;
+    const bool mutual = (flags & HM_FLAG_MUTUAL) && nq > 0 && nt > 0;
+    // Mutual check with the kind::mxf4 core: the forward kernel applies the ratio test to each row's final keys and
+    // marks the best train row of every survivor as a candidate; the swapped pass then computes the best query of the
+    // CANDIDATE train rows only (gathered inside the kernel from a device-side list).  A match (q, t) is mutual iff q
+    // is the best query of t, and only candidates are ever asked -- same result as the full swapped pass, for the
+    // fraction of its work that the ratio test leaves (HM_MUTUAL_FULL=1 forces the full pass, for A/B runs).
+    static const bool full_pass = getenv("HM_MUTUAL_FULL") != nullptr;
+    if (mutual && !full_pass && resolve_variant(variant, nq, nt, batch) == HM_VARIANT_F4) {
+        SelectArgs sel;
+        memset(&sel, 0, sizeof(sel));
+        sel.count = reinterpret_cast<int*>(sel_ws);
+        sel.slot_of = reinterpret_cast<int*>(sel_ws + align_up((size_t)batch * 4));
+        sel.list = reinterpret_cast<int*>(sel_ws + select_zeroed_bytes(nt, batch));
+        sel.nt = nt;
+        sel.use_ratio = (flags & HM_FLAG_RATIO) ? 1 : 0;
+        sel.lut = lut;
+        HM_CUDA_CHECK(cudaMemsetAsync(sel_ws, 0, select_zeroed_bytes(nt, batch), st));
+        p.select = &sel;
+        if ((rc = knn2_dispatch(p, fwd, HM_VARIANT_F4, knn_ws, knn_ws_bytes, st)) != HM_OK) return rc;
+        KnnProblem r{};
+        r.q = train; r.t = query; r.nq = nt; r.nt = nq; r.q_stride = t_stride; r.t_stride = q_stride;
+        r.q_batch_stride = t_batch_stride; r.t_batch_stride = q_batch_stride; r.batch = batch;
+        r.top1 = true;
+        if ((rc = launch_tc_knn1_candidates(r, sel.list, sel.count, bwd, knn_ws, knn_ws_bytes, di.sm_count, st)) != HM_OK) return rc;
+        return launch_filter(fwd, nq, bwd, nt, batch, flags, lut, thr, out_q, out_t, out_d, out_count, st, sel.slot_of);
+    }
     if ((rc = knn2_dispatch(p, fwd, variant, knn_ws, knn_ws_bytes, st)) != HM_OK) return rc;
-    if ((flags & HM_FLAG_MUTUAL) && nq > 0 && nt > 0) {
+    if (mutual) {
         KnnProblem r{};
         r.q = train; r.t = query; r.nq = nt; r.nt = nq; r.q_stride = t_stride; r.t_stride = q_stride;
         r.q_batch_stride = t_batch_stride; r.t_batch_stride = q_batch_stride; r.batch = batch;

@@ -34,13 +34,52 @@ struct KnnProblem {
     int batch;
     unsigned long long train_base;            // added to every trainIdx
     bool top1;                                // only the nearest neighbour is needed (second key may be HM_NO_MATCH)
+    const struct SelectArgs* select;          // tensor-core kind::mxf4 launches only: see SelectArgs
 };
 
 // packed query descriptors handed to the tensor-core launcher (kind::mxf4 expands them inside the k-NN kernel)
 struct QueryBits {
     const uint8_t* bits;
     long long stride, batch_stride;
+    // optional gather + device-side row count (TcParams::q_index / nq_dyn): the candidate pass of the mutual check
+    const int* index;
+    long long index_batch_stride;
+    const int* nq_dyn;
 };
+
+struct RatioLut {
+    unsigned short v[257];
+};
+
+// Ratio test + candidate selection on a row's final keys, run by the k-NN kernel that produced them (row P of
+// /root/reference/feature_matchers.py:34,39 extended by Lowe's test and the mutual check).  A row that
+// passes the ratio test marks its best train row as a CANDIDATE column; the swapped pass of the mutual check then
+// runs only over the candidate rows (hm_match_fused), not over the whole train set.
+struct SelectArgs {
+    int* slot_of;        // [batch][nt], zeroed: slot + 1 once the train row is a candidate (-1 while being assigned)
+    int* list;           // [batch][nt] candidate train rows, arrival order
+    int* count;          // [batch], zeroed
+    long long nt;
+    int use_ratio;
+    RatioLut lut;        // lut[d2] = ceil(ratio * d2): d1 < ratio * d2  <=>  d1 < lut[d2] for integer d1
+};
+
+__device__ __forceinline__ void select_candidate(const SelectArgs& S, int b, ulonglong2 k)
+{
+    if (!S.slot_of || k.x == kNoMatch) return;
+    if (S.use_ratio) {
+        if (k.y == kNoMatch) return;
+        const unsigned d2 = min((unsigned)(k.y >> 32), 256u);
+        if (!((unsigned)(k.x >> 32) < (unsigned)S.lut.v[d2])) return;
+    }
+    const long long t = (long long)(k.x & 0xFFFFFFFFull);
+    int* cell = S.slot_of + (long long)b * S.nt + t;
+    if (atomicCAS(cell, 0, -1) == 0) {                  // first row that names this train row
+        const int s = atomicAdd(S.count + b, 1);
+        S.list[(long long)b * S.nt + s] = (int)t;
+        atomicExch(cell, s + 1);
+    }
+}
 
 struct DeviceInfo {
     int device;
@@ -219,6 +258,11 @@ int fill_exchange_args(ExchangeArgs* x, int world, int rank, void* const* peers,
 size_t tc_workspace_bytes(long long nq, long long nt, int batch, int sm_count, bool with_prepare, int variant);
 int launch_tc_knn2(const KnnProblem& p, unsigned long long* out, void* ws, size_t ws_bytes, int sm_count,
                    int variant, cudaStream_t stream);
+// kind::mxf4 only.  Top-1 of the train rows list[b][0 .. count[b]) (device-side list and count) against all query
+// rows: out[b][slot] = best query of candidate `slot`.  p.q / p.nq = the TRAIN side (gathered), p.t / p.nt = the query
+// side (prepared into the workspace, which must hold tc_workspace_bytes(p.nq, p.nt, ..., with_prepare)).
+int launch_tc_knn1_candidates(const KnnProblem& p, const int* list, const int* count, unsigned long long* out, void* ws,
+                              size_t ws_bytes, int sm_count, cudaStream_t stream);
 
 // epilogues
 int launch_merge_top2(const unsigned long long* keys, int groups, long long rows, unsigned long long* out,
@@ -229,12 +273,10 @@ int launch_exchange_merge(const unsigned long long* local_keys, int local_groups
                           void* const* peers, long long max_rows, unsigned epoch, unsigned long long* out,
                           cudaStream_t stream);
 
-struct RatioLut {
-    unsigned short v[257];
-};
+// slot_of != null: bwd holds one entry per CANDIDATE train row (SelectArgs), train row t at slot_of[t] - 1
 int launch_filter(const unsigned long long* fwd, long long nq, const unsigned long long* bwd, long long nt,
                   int batch, unsigned flags, const RatioLut& lut, int thr_ceil, int* out_q, int* out_t,
-                  int* out_d, int* out_count, cudaStream_t stream);
+                  int* out_d, int* out_count, cudaStream_t stream, const int* slot_of = nullptr);
 
 void describe_tc_launch(long long nq, long long nt, int batch, int sm_count, int variant, bool top1, char* buf, size_t n);
 int launch_gather_points(const int* q_idx, const int* t_idx, const int* count, long long stride, int batch,

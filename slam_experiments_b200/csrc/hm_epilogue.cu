@@ -61,6 +61,7 @@ struct FilterParams {
     int* out_t;
     int* out_d;
     int* out_count;
+    const int* slot_of;              // [batch][nt] candidate slots + 1 (SelectArgs), null = bwd indexed by train row
     RatioLut lut;
 };
 
@@ -108,7 +109,10 @@ __global__ void __launch_bounds__(kFilterThreads) hm_filter_kernel(const FilterP
                 keep = (k.y != kNoMatch) && d1 < (int)P.lut.v[min((unsigned)(k.y >> 32), 256u)];
             }
             if (keep && (P.flags & HM_FLAG_MUTUAL)) {
-                keep = (long long)(bwd[(long long)t1 * 2] & 0xFFFFFFFFull) == r;
+                // bwd is indexed by train row, or -- after the candidate pass -- by the row's candidate slot (a row
+                // that reaches this line passed the ratio test, so the k-NN kernel gave its best train row a slot)
+                const long long slot = P.slot_of ? (long long)P.slot_of[(long long)b * P.nt + t1] - 1 : (long long)t1;
+                keep = slot >= 0 && (long long)(bwd[slot * 2] & 0xFFFFFFFFull) == r;
             }
             if (keep && (P.flags & HM_FLAG_DIST_THRESHOLD)) keep = d1 < limit;
         }
@@ -202,10 +206,11 @@ int launch_exchange_merge(const unsigned long long* local_keys, int local_groups
 
 int launch_filter(const unsigned long long* fwd, long long nq, const unsigned long long* bwd, long long nt,
                   int batch, unsigned flags, const RatioLut& lut, int thr_ceil, int* out_q, int* out_t,
-                  int* out_d, int* out_count, cudaStream_t stream)
+                  int* out_d, int* out_count, cudaStream_t stream, const int* slot_of)
 {
     if (batch <= 0) return HM_OK;
     FilterParams P{};
+    P.slot_of = slot_of;
     P.fwd = fwd; P.bwd = bwd; P.nq = nq; P.nt = nt; P.flags = flags;
     P.out_q = out_q; P.out_t = out_t; P.out_d = out_d; P.out_count = out_count;
     P.lut = lut;

@@ -251,6 +251,13 @@ struct TcParams {
     // for the query side, one launch per k-NN call.
     const uint8_t* qbits;
     long long q_bits_stride, q_bits_batch_stride;
+    // with qbits: query row r of problem b is row q_index[b * q_index_batch_stride + r] of the packed array (a gather
+    // folded into the expansion), and only the first nq_dyn[b] (<= nq) query rows exist -- a row count produced on the
+    // device by an earlier kernel of the same stream.  Clusters whose query blocks lie beyond it return at once.
+    // This is the swapped pass of the mutual check restricted to the candidate train rows (hm_match_fused).
+    const int* q_index;
+    long long q_index_batch_stride;
+    const int* nq_dyn;
     const uint8_t* qprep;            // [batch][q_padded][row bytes]
     const uint8_t* tprep;            // [batch][t_padded][row bytes]
     long long nq, nt;
@@ -277,6 +284,7 @@ struct TcParams {
     // (0,0,0) at entry and exit.  Their ratio is the SM clock actually running under this kernel -- NVML, polled every
     // few ms, keeps reporting the 1965 MHz application clock while the chip runs the tensor pipe at ~1.65-1.75 GHz.
     long long* clock_probe;
+    SelectArgs sel;                  // sel.slot_of != null: ratio test + candidate-column selection on the final keys
     long long* trace;                // development aid (HM_I8_TRACE): per-tile clock64 stamps of CTA 0, else null
     int trace_first;                 // first tile recorded (HM_TRACE_FIRST)
 };
@@ -591,6 +599,11 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     const uint32_t crank = ptx::cluster_ctarank();
     const uint16_t cmask = (uint16_t)((1u << cs) - 1);
     const bool has_a = qb < P.q_blocks_valid;
+    // query rows that exist: P.nq, or the device-side count of a candidate list (the stride of every per-row array
+    // stays P.nq).  A cluster with no row left returns as a whole, before any barrier or TMEM allocation.
+    // (re-evaluated where it is needed instead of being kept in registers across the tile loop)
+    auto rows_present = [&]() -> long long { return P.nq_dyn ? min((long long)__ldg(P.nq_dyn + b), P.nq) : P.nq; };
+    if (P.nq_dyn && (long long)(qb - (int)crank) * kBlockM >= rows_present()) return;
 
     const int tile_begin = split * P.tiles_per_split;
     const int tile_end = min(tile_begin + P.tiles_per_split, P.ntiles);
@@ -640,6 +653,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             // A operand from packed bits: the same swizzled image hm_prepare_f4_kernel writes, straight into shared
             // memory (chunk position -> row and logical chunk as there); rows past nq are +0.0 like the padding
             const uint8_t* qsrc = P.qbits + (long long)b * P.q_bits_batch_stride;
+            const int* qidx = P.q_index ? P.q_index + (long long)b * P.q_index_batch_stride : nullptr;
+            const long long nq_eff = rows_present();
             for (int o = threadIdx.x; o < kBlockM * 8; o += blockDim.x) {
                 const int blk = o >> 10, rem = o & 1023;
                 const int rr = (rem >> 3) & 7;
@@ -647,7 +662,10 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 const int c = (rem & 7) ^ rr;
                 const long long qrow = (long long)qb * kBlockM + blk * kRowBlock + r;
                 uint4 v = make_uint4(0, 0, 0, 0);
-                if (qrow < P.nq) v = expand_bits_e2m1(*reinterpret_cast<const unsigned*>(qsrc + qrow * P.q_bits_stride + c * 4));
+                if (qrow < nq_eff) {
+                    const long long srow = qidx ? (long long)__ldg(qidx + qrow) : qrow;
+                    v = expand_bits_e2m1(*reinterpret_cast<const unsigned*>(qsrc + srow * P.q_bits_stride + c * 4));
+                }
                 reinterpret_cast<uint4*>(smem_a)[o] = v;
             }
             ptx::fence_proxy_async();      // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -821,7 +839,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 if (i < HM_FLOOR_DENSE_TILES || (i & HM_FLOOR_LATE_MASK) == 0) {
                     floor_code = max(floor_code, floor_pending);
                     s.f = C::max2(s.f, C::floor_from(floor_code));
-                    if (row < P.nq) {
+                    if (row < P.nq) {              // (the threshold kernels never run with a device-side row count)
                         unsigned* floor_ptr = P.row_floor + ((long long)b * P.nq + row);
                         const unsigned e = C::valid(s.v2) ? C::encode(s.v2) : 0u;
                         if (e > floor_code) { atomicMax(floor_ptr, e); floor_code = e; }
@@ -958,7 +976,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, kTmemCols);
     }
-    if (my_row >= 0 && my_row < P.nq) {
+    if (my_row >= 0 && my_row < rows_present()) {
         if constexpr (C::kColSplit == 2) {     // fold the upper column half's candidates (u64 min = cv2's order)
             const ulonglong2 o = handover[my_row_in_cta];
             top2_insert(my_keys.x, my_keys.y, o.x);
@@ -966,20 +984,24 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         }
         unsigned long long* out = P.out + (long long)split * P.out_split_stride + ((long long)b * P.nq + my_row) * 2;
         *reinterpret_cast<ulonglong2*>(out) = my_keys;
+        if (!P.counters) select_candidate(P.sel, b, my_keys);      // unsplit launch: these are the row's final keys
     }
     // ---- in-kernel merge of the train splits: the last CTA of this query block folds all partials ----
     if (P.counters) {
         int* flag = reinterpret_cast<int*>(tmem_base_slot + 1);
         if (last_cta_arrives(&P.counters[(long long)b * gridDim.x + qb], (unsigned)P.splits, flag)) {
             const long long row = (long long)qb * kBlockM + threadIdx.x;
-            const bool has_row = threadIdx.x < kBlockM && row < P.nq;
+            const bool has_row = threadIdx.x < kBlockM && row < rows_present();
             ulonglong2 k = make_ulonglong2(kNoMatch, kNoMatch);
             if (has_row) fold_partials(P.out, P.splits, P.out_split_stride, (long long)b * P.nq + row, k.x, k.y);
             // sharded database: push to the peer GPUs, wait for theirs, merge -- still inside this launch
             // (only query blocks that hold rows take part: hm_exchange_merge_kernel on a peer covers exactly
             // ceil(nq / 256) blocks, so both kernels post and wait on the same flags whatever mix of them the ranks run)
             if (P.xch.world > 1 && (long long)qb * kBlockM < P.nq) k = exchange_and_merge(P.xch, row, has_row, k, qb);
-            if (has_row) *reinterpret_cast<ulonglong2*>(P.final_out + ((long long)b * P.nq + row) * 2) = k;
+            if (has_row) {
+                *reinterpret_cast<ulonglong2*>(P.final_out + ((long long)b * P.nq + row) * 2) = k;
+                select_candidate(P.sel, b, k);
+            }
         }
     }
     if (threadIdx.x == 0) cta_mark(P, 4);
@@ -1174,7 +1196,8 @@ template <class C>
 int launch_prepared(const void* qprep, long long nq, const void* tprep, long long nt, int batch,
                     unsigned long long train_base, unsigned long long* out, void* ws, size_t ws_bytes,
                     int sm_count, cudaStream_t stream, const unsigned long long** out_partials,
-                    int* out_groups, const ExchangeArgs* exchange, bool top1 = false, const QueryBits* qbits = nullptr)
+                    int* out_groups, const ExchangeArgs* exchange, bool top1 = false, const QueryBits* qbits = nullptr,
+                    const SelectArgs* select = nullptr)
 {
     HM_CUDA_CHECK(ensure_smem_opt_in<C>());
     const TcPlan pl = plan_tc<C>(nq, nt, batch, sm_count);
@@ -1196,6 +1219,14 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
             return HM_ERR_UNSUPPORTED;
         }
         P.qbits = qbits->bits; P.q_bits_stride = qbits->stride; P.q_bits_batch_stride = qbits->batch_stride;
+        P.q_index = qbits->index; P.q_index_batch_stride = qbits->index_batch_stride; P.nq_dyn = qbits->nq_dyn;
+    }
+    if (select && select->slot_of) {
+        if (keep_partials || (exchange && exchange->world > 1)) {
+            set_error("candidate selection needs final keys of a single GPU");
+            return HM_ERR_INVALID_ARGUMENT;
+        }
+        P.sel = *select;
     }
     P.qprep = static_cast<const uint8_t*>(qprep);
     P.tprep = static_cast<const uint8_t*>(tprep);
@@ -1236,7 +1267,7 @@ int launch_prepared(const void* qprep, long long nq, const void* tprep, long lon
     }
     // shared row thresholds: the CTAs (and, with kColSplit == 2, the two column-half warps) of a query row
     bool zero_block = false;
-    const bool floor_eligible = !top1 && pl.tiles_per_split <= floor_max_tiles() &&
+    const bool floor_eligible = !top1 && !P.nq_dyn && pl.tiles_per_split <= floor_max_tiles() &&
                                 (pl.splits > 1 || (C::kColSplit > 1 && pl.ntiles >= floor_min_tiles_unsplit()));
     if (floor_eligible) {
         P.row_floor = reinterpret_cast<unsigned*>(reinterpret_cast<uint8_t*>(counters) + counters_bytes(pl.qblocks * batch));
@@ -1362,8 +1393,12 @@ int launch_knn2_of(const KnnProblem& p, unsigned long long* out, void* ws, size_
     }
     rc = launch_prepare_of<C>(p.t, p.nt, p.t_stride, p.t_batch_stride, p.batch, tprep, stream);
     if (rc != HM_OK) return rc;
+    if (p.select && !C::kScales) {
+        set_error("candidate selection exists for the kind::mxf4 core only");
+        return HM_ERR_UNSUPPORTED;
+    }
     return launch_prepared<C>(qprep, p.nq, tprep, p.nt, p.batch, p.train_base, out, ws, head, sm_count, stream, nullptr,
-                              nullptr, nullptr, p.top1, &qb);
+                              nullptr, nullptr, p.top1, &qb, p.select);
 }
 
 }  // namespace
@@ -1428,6 +1463,26 @@ int launch_tc_knn2_resident(const uint8_t* qbits, long long nq, long long q_stri
     if (rc != HM_OK) return rc;
     return launch_prepared<CoreI8>(qprep, nq, tprep, nt, 1, train_base, out, ws, head, sm_count, stream, nullptr, nullptr,
                                    exchange);
+}
+
+int launch_tc_knn1_candidates(const KnnProblem& p, const int* list, const int* count, unsigned long long* out, void* ws,
+                              size_t ws_bytes, int sm_count, cudaStream_t stream)
+{
+    using C = CoreF4;
+    const size_t need = workspace_bytes_of<C>(p.nq, p.nt, p.batch, sm_count, true);
+    if (!ws || ws_bytes < need) {
+        set_error("workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+        return HM_ERR_WORKSPACE;
+    }
+    const size_t head = workspace_bytes_of<C>(p.nq, p.nt, p.batch, sm_count, false);
+    uint8_t* tprep = static_cast<uint8_t*>(ws) + head + (size_t)padded_rows<C>(p.nq) * C::kRowBytes * p.batch;
+    int rc = launch_prepare_of<C>(p.t, p.nt, p.t_stride, p.t_batch_stride, p.batch, tprep, stream);
+    if (rc != HM_OK) return rc;
+    QueryBits qb{};
+    qb.bits = p.q; qb.stride = p.q_stride; qb.batch_stride = p.q_batch_stride;
+    qb.index = list; qb.index_batch_stride = p.nq; qb.nq_dyn = count;
+    return launch_prepared<C>(nullptr, p.nq, tprep, p.nt, p.batch, 0, out, ws, head, sm_count, stream, nullptr, nullptr,
+                              nullptr, true, &qb);
 }
 
 // "kernel grid=(x,y,z) cluster=c" of the launch the given shape would get (introspection for bench / docs)
