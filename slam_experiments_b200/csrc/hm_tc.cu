@@ -41,6 +41,8 @@
 #include <mutex>
 #include <type_traits>
 
+#include <cuda_fp16.h>
+
 #include "hm_common.cuh"
 #include "hm_tcgen05.cuh"
 
@@ -75,23 +77,21 @@ struct CoreI8 {
     static constexpr int kStages = 4;                        // 4 x 32 KB in flight
     static constexpr int kUnits = 4;                         // accumulator units of kTileN TMEM columns
     static constexpr int kColSplit = 1;                      // 8 epilogue warps: the MMA (and the power cap) paces this core
+    static constexpr bool kRegisterHandover = false;         // 10 warps: 168 registers per thread as launched
     static constexpr bool kScales = false;
     static constexpr int kPrologueTiles = 45;                // fixed per-CTA cost in tile times (split planning; half the kind::mxf4 figure: its tiles last twice as long)
     static __device__ __forceinline__ Acc lowest() { return INT_MIN; }
     static __device__ __forceinline__ Acc from_bits(uint32_t x) { return (int)x; }
     static __device__ __forceinline__ Acc max3(Acc a, Acc b, Acc c) { return __vimax3_s32(a, b, c); }
     static __device__ __forceinline__ Acc max2(Acc a, Acc b) { return max(a, b); }
-    static __device__ __forceinline__ bool valid(Acc v) { return v != INT_MIN; }
+    static __device__ __forceinline__ bool valid(Acc v) { return v >= -256; }
     static __device__ __forceinline__ unsigned distance(Acc v) { return (unsigned)((256 - v) >> 1); }
     static __device__ __forceinline__ unsigned encode(Acc v) { return (unsigned)(v + 257); }          // 1..513, 0 = none
     static __device__ __forceinline__ Acc floor_from(unsigned e) { return (int)e - 259; }             // dot - 2
-    // dot * 64 + (63 - j): max over these keys = largest dot, ties to the lowest column j (< 64)
-    using Key = int;
-    static __device__ __forceinline__ Key packed_key(uint32_t bits, int j) { return (int)bits * 64 + (63 - j); }
-    static __device__ __forceinline__ Key kmax(Key a, Key b) { return max(a, b); }
-    static __device__ __forceinline__ Key kmin(Key a, Key b) { return min(a, b); }
-    static __device__ __forceinline__ Key kmax3(Key a, Key b, Key c) { return __vimax3_s32(a, b, c); }
-    static __device__ __forceinline__ int key_bits(Key k) { return k; }
+    // two dots (|dot| <= 256, or the "no column" marker) in one register: the saved values of a candidate group
+    static __device__ __forceinline__ uint32_t pack2(uint32_t lo, uint32_t hi) { return ((uint32_t)max((int)lo, -32768) & 0xFFFFu) | ((uint32_t)max((int)hi, -32768) << 16); }
+    static __device__ __forceinline__ Acc unpack(uint32_t p, int hi) { return hi ? (int)p >> 16 : (int)(short)(p & 0xFFFFu); }
+    static constexpr uint32_t kLowestBits = 0x80000000u;
 };
 
 struct CoreF4 {
@@ -119,6 +119,7 @@ struct CoreF4 {
     // bound (ncu r01j: issue slots 37 %, ALU 46 %, top stalls wait / long scoreboard) at 1087 cycles per
     // tile while the MMAs need 512
     static constexpr int kColSplit = 2;
+    static constexpr bool kRegisterHandover = true;
     static constexpr bool kScales = true;
     // fixed cost of a CTA in steady-state tile times: launch + pipeline fill, the branch-free first tiles and the
     // slow early tiles before the thresholds settle.  Measured (2000 queries, 512 k ... 8.19 M train rows):
@@ -132,21 +133,31 @@ struct CoreF4 {
     static __device__ __forceinline__ unsigned distance(Acc v) { return (unsigned)((256 - (int)v) >> 1); }
     static __device__ __forceinline__ unsigned encode(Acc v) { return (unsigned)((int)v + 257); }
     static __device__ __forceinline__ Acc floor_from(unsigned e) { return (float)((int)e - 259); }
-    // dot * 64 + (63 - j) as a FLOAT: one FFMA (FMA pipe; the tournament below saturates the ALU pipe), exact because
-    // |key| < 2^15; ordering and ties as for the integer key
-    using Key = float;
-    static __device__ __forceinline__ Key packed_key(uint32_t bits, int j) { return fmaf(__uint_as_float(bits), 64.0f, (float)(63 - j)); }
-    static __device__ __forceinline__ Key kmax(Key a, Key b) { return fmaxf(a, b); }
-    static __device__ __forceinline__ Key kmin(Key a, Key b) { return fminf(a, b); }
-    static __device__ __forceinline__ Key kmax3(Key a, Key b, Key c) { return fmaxf(fmaxf(a, b), c); }
-    static __device__ __forceinline__ int key_bits(Key k) { return (int)k; }
+    // f16x2: exact for integers up to 2048, and -inf stays -inf; one F2FP per pair
+    static __device__ __forceinline__ uint32_t pack2(uint32_t lo, uint32_t hi)
+    {
+        const __half2 h = __floats2half2_rn(__uint_as_float(lo), __uint_as_float(hi));
+        return *reinterpret_cast<const uint32_t*>(&h);
+    }
+    static __device__ __forceinline__ Acc unpack(uint32_t p, int hi)
+    {
+        const __half2 h = *reinterpret_cast<const __half2*>(&p);
+        return hi ? __high2float(h) : __low2float(h);
+    }
+    static constexpr uint32_t kLowestBits = 0xFF800000u;
 };
 
 template <class C> __host__ __device__ constexpr int row_block_bytes() { return kRowBlock * C::kRowBytes; }
 template <class C> __host__ __device__ constexpr int a_bytes() { return kMBlocks * row_block_bytes<C>(); }
 template <class C> __host__ __device__ constexpr int b_stage_bytes() { return C::kTileN * C::kRowBytes; }
 template <class C> __host__ __device__ constexpr int epilogue_warps() { return 4 * kMBlocks * C::kColSplit; }
-template <class C> __host__ __device__ constexpr int threads() { return 32 * (2 + epilogue_warps<C>()); }
+// kind::mxf4: 16 epilogue warps + producer + issuer = 18 warps put five warps on two of the four SM sub-partitions, which
+// caps every thread at 96 registers (16384 / (5 * 32) rounded down to 8).  The CTA is therefore launched with a full
+// fifth warpgroup -- producer, issuer and two idle warps -- that hands registers to the epilogue warps at entry
+// (setmaxnreg: 4 x 32 + 16 x 112 = 20 x 96 registers per thread-slot): the scan keeps 64 accumulator values, the
+// running top-2 and the saved dots of two candidate groups in registers without spilling.
+template <class C> __host__ __device__ constexpr int control_warps() { return C::kRegisterHandover ? 4 : 2; }
+template <class C> __host__ __device__ constexpr int threads() { return 32 * (control_warps<C>() + epilogue_warps<C>()); }
 // + 256 B of barriers, + 4 KB where the epilogue warps of the upper column halves hand over their keys
 constexpr int kHandoverBytes = kBlockM * 16;
 constexpr int kBarrierBytes = 512;
@@ -341,18 +352,28 @@ __device__ __forceinline__ void trace_mark(const TcParams& P, int tile, int slot
 #endif
 }
 
+// Running top-2 of one query row at GROUP granularity.  A group is 8 consecutive train columns.  The scan keeps the
+// two groups with the largest maxima (earliest group on ties) and a copy of their 8 dots each, packed two per
+// register; the exact (distance, trainIdx) top-2 is taken from those 16 saved dots once, at the end of the CTA.
+// Why that is exact: the best column (largest dot, lowest index) lies in the earliest group whose maximum is the
+// overall maximum = g1.  Any group other than g1 and g2 has a maximum <= v2 and, on equality, a later position than
+// g2, so each of its columns loses against g1's best AND against g2's best: the second-best column lies in g1 or g2.
+// What this buys: a candidate costs one compare per GROUP and ~15 predicated instructions for the group that holds
+// it, instead of a compare-and-insert chain over its 8 columns -- the path every warp is on while the thresholds are
+// still low (CTAs that see fewer than ~10^4 columns: C2, C3, C5, 8-GPU shards never leave it).
 template <class Acc>
 struct Top2 {
-    Acc v1, v2;                      // best / second-best dot (larger = closer)
-    unsigned i1, i2;                 // train row local to this CTA's range
+    Acc v1, v2;                      // largest / second-largest group maximum (larger dot = closer)
+    unsigned i1, i2;                 // first column of those groups, local to this CTA's range
+    uint32_t sa[4], sb[4];           // their 8 dots (C::pack2)
     // Filter threshold f = max(v2, shared) where `shared` = (second-best dot some CTA of this row has already
-    // published, see TcParams::row_floor) - 2.  A column can only matter if its dot is > v2 (to enter the local
+    // published, see TcParams::row_floor) - 2.  A group can only matter if its maximum is > v2 (to enter the local
     // top-2) and >= the published second best (to enter the row's final top-2; dots are even, so "> shared"):
     // one compare against f skips everything else.  v2 only grows, so after an insertion
     // max(v2_new, shared) = max(v2_new, f_old) and `shared` itself need not be kept.
     Acc f;
 #if HM_TC_TRACE
-    unsigned slow;                   // trace builds: warp-level entries into the exact-insertion path
+    unsigned slow;                   // trace builds: warp-level entries into the insertion path
 #endif
 };
 
@@ -361,6 +382,17 @@ __device__ __forceinline__ void bounded_wait(uint64_t* bar, uint32_t parity, int
     uint32_t spins = 0;
     while (!ptx::mbar_try_wait(bar, parity)) {
         if (++spins > kSpinLimit) {          // a protocol bug must not hang the GPU
+            if (error_flag) atomicExch(error_flag, 1);
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ void bounded_wait_addr(uint32_t bar_addr, uint32_t parity, int* error_flag)
+{
+    uint32_t spins = 0;
+    while (!ptx::mbar_try_wait_addr(bar_addr, parity)) {
+        if (++spins > kSpinLimit) {
             if (error_flag) atomicExch(error_flag, 1);
             __trap();
         }
@@ -383,17 +415,16 @@ __device__ __forceinline__ void tmem_ld_fence64(uint32_t (&a)[64])
     asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R8(a, 0), HM_R8(a, 8), HM_R8(a, 16), HM_R8(a, 24), HM_R8(a, 32), HM_R8(a, 40), HM_R8(a, 48), HM_R8(a, 56) : : "memory");
 }
 
-// 32 consecutive train columns of one query row.  Fast path: 3-input-max trees give the maximum
-// of each group of 8 columns and of the whole chunk; one compare + branch per chunk against the
-// running second best decides whether anything can change the top-2.  Only then are the groups
-// revisited, and the exact (value, index) insertion runs for the groups that still qualify.
-// Strict '>' keeps the lowest train index on ties because columns are visited in ascending order.
+// 32 (16) consecutive train columns of one query row.  Fast path: 3-input-max trees give the maximum of each group
+// of 8 columns and of the whole chunk; one compare + branch per chunk against the threshold decides whether anything
+// can change the top-2.  Only then are the group maxima revisited; a group above the threshold is inserted into the
+// top-2 of groups together with a packed copy of its dots.  Strict '>' in ascending column order keeps the earliest
+// group on ties, which is what the lowest-trainIdx rule needs (see Top2).
 // kMode: 0 = top-2, 1 = top-2 with the shared row threshold, 2 = top-1 only (the swapped pass of the mutual
-// check needs nothing else: the threshold is then the best dot itself, so the exact-insertion path fires
-// about half as often and is shorter)
+// check needs nothing else: the threshold is then the best dot itself, so the insertion path fires about half as
+// often)
 template <class C, int kMode, int kGroups = 4>
-__device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, unsigned limit,
-                                           Top2<typename C::Acc>& s)
+__device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, Top2<typename C::Acc>& s)
 {
     using Acc = typename C::Acc;
     Acc gm[4];
@@ -412,128 +443,46 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, 
 #endif
 #pragma unroll
         for (int g = 0; g < kGroups; ++g) {
-            if (gm[g] > (kFloor ? s.f : kTop1 ? s.v1 : s.v2)) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const Acc x = C::from_bits(r[g * 8 + e]);
-                    const unsigned idx = colbase + g * 8 + e;
-                    if (x > (kFloor ? s.f : kTop1 ? s.v1 : s.v2) && idx < limit) {
-                        if (kTop1) {
-                            s.v1 = x;    s.i1 = idx;
-                        } else if (x > s.v1) {
-                            s.v2 = s.v1; s.i2 = s.i1;
-                            s.v1 = x;    s.i1 = idx;
-                        } else {
-                            s.v2 = x;    s.i2 = idx;
-                        }
-                        if (kFloor) s.f = C::max2(s.v2, s.f);
+            const Acc x = gm[g];
+            if (x > (kFloor ? s.f : kTop1 ? s.v1 : s.v2)) {
+                const int o = g * 8;
+                const uint32_t p0 = C::pack2(r[o], r[o + 1]), p1 = C::pack2(r[o + 2], r[o + 3]);
+                const uint32_t p2 = C::pack2(r[o + 4], r[o + 5]), p3 = C::pack2(r[o + 6], r[o + 7]);
+                const unsigned idx = colbase + o;
+                if (kTop1 || x > s.v1) {
+                    if (!kTop1) {
+                        s.v2 = s.v1; s.i2 = s.i1;
+                        s.sb[0] = s.sa[0]; s.sb[1] = s.sa[1]; s.sb[2] = s.sa[2]; s.sb[3] = s.sa[3];
                     }
+                    s.v1 = x; s.i1 = idx;
+                    s.sa[0] = p0; s.sa[1] = p1; s.sa[2] = p2; s.sa[3] = p3;
+                } else {
+                    s.v2 = x; s.i2 = idx;
+                    s.sb[0] = p0; s.sb[1] = p1; s.sb[2] = p2; s.sb[3] = p3;
                 }
+                if (kFloor) s.f = C::max2(s.v2, s.f);
             }
         }
     }
 }
 
-// 64 consecutive columns with ONE compare + branch: the fast path of an item is one straight run of code (the two
-// 32-column chunks above each carry their own exact-insertion block, which scatters the hot loop over four code
-// regions 5 KB apart).
-template <class C, int kMode>
-__device__ __forceinline__ void scan_item64(const uint32_t* r, unsigned colbase, unsigned limit, Top2<typename C::Acc>& s)
-{
-    using Acc = typename C::Acc;
-    constexpr bool kFloor = kMode == 1, kTop1 = kMode == 2;
-    Acc gm[8];
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-        const int o = g * 8;
-        gm[g] = C::max3(C::max3(C::from_bits(r[o]), C::from_bits(r[o + 1]), C::from_bits(r[o + 2])),
-                        C::max3(C::from_bits(r[o + 3]), C::from_bits(r[o + 4]), C::from_bits(r[o + 5])),
-                        C::max2(C::from_bits(r[o + 6]), C::from_bits(r[o + 7])));
-    }
-    const Acc m = C::max3(C::max3(gm[0], gm[1], gm[2]), C::max3(gm[3], gm[4], gm[5]), C::max2(gm[6], gm[7]));
-    if (m > (kFloor ? s.f : kTop1 ? s.v1 : s.v2)) {
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            if (gm[g] > (kFloor ? s.f : kTop1 ? s.v1 : s.v2)) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const Acc x = C::from_bits(r[g * 8 + e]);
-                    const unsigned idx = colbase + g * 8 + e;
-                    if (x > (kFloor ? s.f : kTop1 ? s.v1 : s.v2) && idx < limit) {
-                        if (kTop1) {
-                            s.v1 = x;    s.i1 = idx;
-                        } else if (x > s.v1) {
-                            s.v2 = s.v1; s.i2 = s.i1;
-                            s.v1 = x;    s.i1 = idx;
-                        } else {
-                            s.v2 = x;    s.i2 = idx;
-                        }
-                        if (kFloor) s.f = C::max2(s.v2, s.f);
-                    }
-                }
-            }
-        }
-    }
-}
-
-// Cold tiles.  A CTA starts with an empty top-2, so in its first tiles nearly every 8-column group holds a candidate
-// for SOME row of the warp and the thresholded scan above degenerates to its insertion path for all 32 rows (~8
-// predicated instructions per element; the pipeline traces show 5000+ cycles per tile against 512 of MMA).  For those
-// tiles the top-2 of the item is taken branch-free instead: every element becomes a packed key (dot, column) with
-// one add + one multiply-add on the FMA pipe, a min/max tournament (2.5 ALU operations per element) leaves the two
-// best keys, and only those two go through the exact insertion.  Ties: the key prefers the lower column, and the
-// strict '>' of the insertion keeps earlier tiles -- the same lowest-trainIdx rule as the scan.
+// columns at or beyond `limit` (the padding rows of the last train tile are +0.0: dot 0) must never win
 template <class C, int kN>
-__device__ __forceinline__ void cold_item(const uint32_t* r, unsigned colbase, Top2<typename C::Acc>& s, bool top1_only)
+__device__ __forceinline__ void mask_tail(uint32_t* r, unsigned colbase, unsigned limit)
 {
-    static_assert(kN <= 64 && (kN & (kN - 1)) == 0, "6 bits of column");
-    using Key = typename C::Key;
-    Key hi[kN / 2], lo[kN / 2];
+    if (colbase + kN > limit) {
 #pragma unroll
-    for (int p = 0; p < kN / 2; ++p) {
-        const Key a = C::packed_key(r[2 * p], 2 * p), b = C::packed_key(r[2 * p + 1], 2 * p + 1);
-        hi[p] = C::kmax(a, b);
-        lo[p] = C::kmin(a, b);
+        for (int j = 0; j < kN; ++j)
+            if (colbase + j >= limit) r[j] = C::kLowestBits;
     }
-#pragma unroll
-    for (int n = kN / 2; n > 1; n >>= 1) {
-#pragma unroll
-        for (int p = 0; p < n / 2; ++p) {
-            const Key h1 = hi[2 * p], h2 = hi[2 * p + 1];
-            lo[p] = C::kmax3(C::kmin(h1, h2), lo[2 * p], lo[2 * p + 1]);
-            hi[p] = C::kmax(h1, h2);
-        }
-    }
-#pragma unroll
-    for (int c = 0; c < 2; ++c) {
-        const int key = C::key_bits(c == 0 ? hi[0] : lo[0]);       // dot * 64 + (63 - column): >> 6 floors, & 63 is the rest
-        const typename C::Acc x = (typename C::Acc)(key >> 6);
-        const unsigned idx = colbase + 63u - (unsigned)(key & 63);
-        if (top1_only) {
-            if (c == 0 && x > s.v1) { s.v1 = x; s.i1 = idx; }
-        } else if (x > s.v1) {
-            s.v2 = s.v1; s.i2 = s.i1;
-            s.v1 = x;    s.i1 = idx;
-        } else if (x > s.v2) {
-            s.v2 = x;    s.i2 = idx;
-        }
-    }
-    s.f = C::max2(s.f, s.v2);
 }
-// first tiles of every CTA that take the branch-free path (HM_COLD_TILES overrides for experiments)
-#ifndef HM_COLD_TILES
-#define HM_COLD_TILES 6
-#endif
-// tiles of a CTA during which the shared row thresholds are refreshed every tile (every 4th afterwards)
+
+// tiles of a CTA during which the shared row thresholds are refreshed every tile (every 16th afterwards)
 #ifndef HM_FLOOR_DENSE_TILES
 #define HM_FLOOR_DENSE_TILES 32
 #endif
 #ifndef HM_FLOOR_LATE_MASK
 #define HM_FLOOR_LATE_MASK 15
-#endif
-// 1: the kind::mxf4 epilogue scans its 64 columns with one compare + branch (scan_item64), 0: as two 32-column chunks
-#ifndef HM_SCAN_FLAT64
-#define HM_SCAN_FLAT64 0
 #endif
 
 // half `h` (0 / 1) of the MMAs of one (tile, query block) item: kSlabs * 2 instructions
@@ -579,6 +528,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     uint64_t* tmem_full_bar = bars + 2 * kStages + 1;      // [kUnits] unit complete
     uint64_t* tmem_empty_bar = tmem_full_bar + kUnits;     // [kUnits] unit drained by its epilogue warps
     uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + kUnits);
+    uint32_t* smem_base_slot = tmem_base_slot + 2;         // shared address of `smem` (see lds_volatile_u32)
     ulonglong2* handover = reinterpret_cast<ulonglong2*>(smem + kABytes + kStages * kBStageBytes + kBarrierBytes);   // [kBlockM]
 
     // broadcast from lane 0: lets ptxas treat the warp index (and the role branches on it) as warp-uniform
@@ -616,7 +566,11 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     constexpr int kProducerWarp = kIssuerLast ? epilogue_warps<C>() : 0;
     constexpr int kIssuerWarp = kIssuerLast ? epilogue_warps<C>() + 1 : 1;
     constexpr int kFirstEpiWarp = kIssuerLast ? 0 : 2;
+    static_assert(kIssuerLast || !C::kRegisterHandover, "the control warps must form the last warpgroup");
+    static_assert(!C::kRegisterHandover || (epilogue_warps<C>() == 16 && threads<C>() == 640),
+                  "the register budget (4 x 32 + 16 x 112 = 20 x 96) assumes 20 warps launched at 96 registers");
     if (warp == kProducerWarp && lane == 0) {
+        *smem_base_slot = ptx::smem_u32(smem);
         for (int i = 0; i < kStages; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
             ptx::mbar_init(&empty_bar[i], cs);           // one (multicast) commit per CTA of the cluster
@@ -680,7 +634,9 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     long long my_row = -1;                                      // >= 0: this thread writes the row's keys
     int my_row_in_cta = 0;
 
-    if (warp == kProducerWarp) {
+    // The three roles and the common tail are lambdas so that the kind::mxf4 core can run the control warpgroup and the
+    // epilogue warps as two separate straight-line paths with different register budgets (see the dispatch below).
+    auto run_producer = [&]() {
         // ===== producer: bulk async copies global -> shared =====
         if (lane == 0) {
             if (has_a && !P.qbits) {
@@ -704,7 +660,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 else        ptx::bulk_g2s(dst, src, piece, &full_bar[stage]);
             }
         }
-    } else if (warp == kIssuerWarp) {
+    };
+    auto run_issuer = [&]() {
         // ===== MMA issuer =====
         // tcgen05.mma issue blocks while the tensor-core queue is full, so every barrier round trip
         // (~100-150 cycles) taken between two groups of MMAs is a bubble in the tensor pipe.  The
@@ -806,7 +763,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             sphase ^= (kPeriod / kStages) & 1;
         }
         __syncwarp();
-    } else {
+    };
+    auto run_epilogue = [&]() {
         // ===== epilogue: TMEM -> registers, running top-2 per query row =====
         constexpr int kCols = kTileN / C::kColSplit;      // train columns of a tile this warp scans
         const int quarter = warp & 3;                     // TMEM lanes [32*quarter, +32) belong to this warp
@@ -817,6 +775,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         Top2<Acc> s;
         s.v1 = s.v2 = C::lowest();
         s.i1 = s.i2 = 0;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s.sa[e] = s.sb[e] = 0;
         s.f = C::floor_from(0);                           // below every possible dot
 #if HM_TC_TRACE
         s.slow = 0;
@@ -824,6 +784,10 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         unsigned floor_code = 0;                          // largest threshold code read or published so far
         const long long first_row = (long long)tile_begin * kTileN;
         const unsigned limit = (unsigned)min((long long)my_tiles * kTileN, P.nt - first_row);
+        // barrier addresses of the tile loop, derived from an opaque copy of the shared-memory base
+        const uint32_t bars_addr = ptx::lds_volatile_u32(ptx::smem_u32(smem_base_slot)) + kABytes + kStages * kBStageBytes;
+        const uint32_t unit_full_addr = bars_addr + (2 * kStages + 1) * 8;
+        const uint32_t unit_empty_addr = unit_full_addr + kUnits * 8;
         int unit = mblk;                                  // (2 * i + mblk) % kUnits
         uint32_t unit_use = 0;                            // (2 * i + mblk) / kUnits
         // Shared row thresholds (kFloor): called between the issue of a tile's TMEM load and its wait.  A refresh folds in
@@ -848,11 +812,8 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 }
             }
         };
-        // one tile; `cold` (a compile-time tag) selects the branch-free top-2 of the first tiles, whose code then sits
-        // in its own loop in front of the steady-state loop instead of inside it
-        auto process_tile = [&](int i, auto cold) {
-            constexpr bool kCold = decltype(cold)::value;
-            bounded_wait(&tmem_full_bar[unit], unit_use & 1, P.error_flag);
+        auto process_tile = [&](int i) {
+            bounded_wait_addr(unit_full_addr + unit * 8, unit_use & 1, P.error_flag);
 #if HM_TC_TRACE == 2
             if (warp == kFirstEpiWarp && lane == 0 && (i == 8 || i == 32 || i == 64 || i == 192)) cta_mark(P, i == 8 ? 5 : i == 32 ? 6 : i == 64 ? 7 : 8);
 #endif
@@ -873,18 +834,17 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 // the accumulator unit is in registers: release it before the scan
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-                if (kCold && colbase + kCols <= limit) {
-                    cold_item<C, 32>(r0, colbase, s, kMode == 2);
-                    cold_item<C, 32>(r1, colbase + 32, s, kMode == 2);
-                    cold_item<C, 32>(r2, colbase + 64, s, kMode == 2);
-                    cold_item<C, 32>(r3, colbase + 96, s, kMode == 2);
-                } else {
-                    scan_chunk<C, kMode>(r0, colbase, limit, s);
-                    scan_chunk<C, kMode>(r1, colbase + 32, limit, s);
-                    scan_chunk<C, kMode>(r2, colbase + 64, limit, s);
-                    scan_chunk<C, kMode>(r3, colbase + 96, limit, s);
+                if (lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
+                if (colbase + kCols > limit) {            // last tile of the train set only
+                    mask_tail<C, 32>(r0, colbase, limit);
+                    mask_tail<C, 32>(r1, colbase + 32, limit);
+                    mask_tail<C, 32>(r2, colbase + 64, limit);
+                    mask_tail<C, 32>(r3, colbase + 96, limit);
                 }
+                scan_chunk<C, kMode>(r0, colbase, s);
+                scan_chunk<C, kMode>(r1, colbase + 32, s);
+                scan_chunk<C, kMode>(r2, colbase + 64, s);
+                scan_chunk<C, kMode>(r3, colbase + 96, s);
             } else {
                 if constexpr (kCols == 64) {
                     uint32_t r[64];
@@ -895,7 +855,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
 #endif
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
+                    if (lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
 #if HM_TC_EXPERIMENT != 0
                     unit += 2;
                     if (unit >= kUnits) { unit -= kUnits; ++unit_use; }
@@ -905,16 +865,9 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     // warp-uniform votes around the insertion path 871; software pipelining over half items -- two
                     // 32-register buffers, the next item's first half loaded while this item's second half is
                     // scanned -- 882)
-                    if (kCold && colbase + kCols <= limit) {
-                        cold_item<C, 64>(r, colbase, s, kMode == 2);
-                    } else {
-#if HM_SCAN_FLAT64
-                        scan_item64<C, kMode>(r, colbase, limit, s);
-#else
-                        scan_chunk<C, kMode>(r, colbase, limit, s);
-                        scan_chunk<C, kMode>(r + 32, colbase + 32, limit, s);
-#endif
-                    }
+                    mask_tail<C, 64>(r, colbase, limit);
+                    scan_chunk<C, kMode>(r, colbase, s);
+                    scan_chunk<C, kMode>(r + 32, colbase + 32, s);
                 } else if constexpr (kCols == 32) {
                     uint32_t r[32];
                     ptx::tmem_ld_32x32(taddr, r);
@@ -922,8 +875,9 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(r) : : "memory");
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-                    scan_chunk<C, kMode>(r, colbase, limit, s);
+                    if (lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
+                    mask_tail<C, 32>(r, colbase, limit);
+                    scan_chunk<C, kMode>(r, colbase, s);
                 } else {
                     static_assert(kCols == 64 || kCols == 48, "column split");
                     uint32_t r0[32], r1[16];
@@ -933,23 +887,19 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     tmem_ld_fence48(r0, r1);
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[unit]);
-                    scan_chunk<C, kMode>(r0, colbase, limit, s);
-                    scan_chunk<C, kMode, 2>(r1, colbase + 32, limit, s);
+                    if (lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
+                    mask_tail<C, 32>(r0, colbase, limit);
+                    mask_tail<C, 16>(r1, colbase + 32, limit);
+                    scan_chunk<C, kMode>(r0, colbase, s);
+                    scan_chunk<C, kMode, 2>(r1, colbase + 32, s);
                 }
             }
             unit += 2;
             if (unit >= kUnits) { unit -= kUnits; ++unit_use; }
             if (warp == kFirstEpiWarp && lane == 0) trace_mark(P, i, 4);   // epilogue: buffer released
         };
-        {
-            int i = 0;
-            const int ncold = min(my_tiles, HM_COLD_TILES);
 #pragma unroll 1
-            for (; i < ncold; ++i) process_tile(i, std::true_type{});
-#pragma unroll 1
-            for (; i < my_tiles; ++i) process_tile(i, std::false_type{});
-        }
+        for (int i = 0; i < my_tiles; ++i) process_tile(i);
         if (warp == kFirstEpiWarp && lane == 0) cta_mark(P, 2);
 #if HM_TC_TRACE
         if (P.trace) {   // slot 9: warp-chunks of this CTA in which at least one lane took the exact-insertion path; slot 10: lane events
@@ -961,55 +911,90 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         }
 #endif
         const unsigned long long gbase = P.train_base + (unsigned long long)first_row;
-        my_keys.x = C::valid(s.v1) ? ((unsigned long long)C::distance(s.v1) << 32) | (gbase + s.i1) : kNoMatch;
-        my_keys.y = (kMode != 2 && C::valid(s.v2)) ? ((unsigned long long)C::distance(s.v2) << 32) | (gbase + s.i2) : kNoMatch;
+        // exact top-2 from the saved dots of the two best groups (u64 min over (distance, trainIdx) keys = cv2's order)
+        auto fold_group = [&](Acc v, unsigned i0, const uint32_t (&p)[4]) {
+            if (!C::valid(v)) return;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const Acc x = C::unpack(p[e >> 1], e & 1);
+                if (C::valid(x)) top2_insert(my_keys.x, my_keys.y, ((unsigned long long)C::distance(x) << 32) | (gbase + i0 + e));
+            }
+        };
+        fold_group(s.v1, s.i1, s.sa);
+        if (kMode != 2) fold_group(s.v2, s.i2, s.sb);
+        else my_keys.y = kNoMatch;
         if (half == 1) handover[row_in_cta] = my_keys;    // merged by the warp of the lower column half below
         else my_row = row;
         my_row_in_cta = row_in_cta;
-    }
+    };
 
-    ptx::tc_fence_before();
-    if (cs > 1) ptx::cluster_sync();   // no CTA leaves while peers may still signal its barriers
-    else __syncthreads();
-    if (threadIdx.x == 0) cta_mark(P, 3);
-    if (warp == kIssuerWarp) {
-        ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, kTmemCols);
-    }
-    if (my_row >= 0 && my_row < rows_present()) {
-        if constexpr (C::kColSplit == 2) {     // fold the upper column half's candidates (u64 min = cv2's order)
-            const ulonglong2 o = handover[my_row_in_cta];
-            top2_insert(my_keys.x, my_keys.y, o.x);
-            top2_insert(my_keys.x, my_keys.y, o.y);
+    // common tail; kWorker = false for the control warps, which only take part in the barriers
+    auto run_tail = [&](auto worker_tag) {
+        constexpr bool kWorker = decltype(worker_tag)::value;
+        ptx::tc_fence_before();
+        if (cs > 1) ptx::cluster_sync();   // no CTA leaves while peers may still signal its barriers
+        else __syncthreads();
+        if (kWorker && threadIdx.x == 0) cta_mark(P, 3);
+        if (warp == kIssuerWarp) {
+            ptx::tc_fence_after();
+            ptx::tmem_dealloc(tmem_base, kTmemCols);
         }
-        unsigned long long* out = P.out + (long long)split * P.out_split_stride + ((long long)b * P.nq + my_row) * 2;
-        *reinterpret_cast<ulonglong2*>(out) = my_keys;
-        if (!P.counters) select_candidate(P.sel, b, my_keys);      // unsplit launch: these are the row's final keys
-    }
-    // ---- in-kernel merge of the train splits: the last CTA of this query block folds all partials ----
-    if (P.counters) {
-        int* flag = reinterpret_cast<int*>(tmem_base_slot + 1);
-        if (last_cta_arrives(&P.counters[(long long)b * gridDim.x + qb], (unsigned)P.splits, flag)) {
-            const long long row = (long long)qb * kBlockM + threadIdx.x;
-            const bool has_row = threadIdx.x < kBlockM && row < rows_present();
-            ulonglong2 k = make_ulonglong2(kNoMatch, kNoMatch);
-            if (has_row) fold_partials(P.out, P.splits, P.out_split_stride, (long long)b * P.nq + row, k.x, k.y);
-            // sharded database: push to the peer GPUs, wait for theirs, merge -- still inside this launch
-            // (only query blocks that hold rows take part: hm_exchange_merge_kernel on a peer covers exactly
-            // ceil(nq / 256) blocks, so both kernels post and wait on the same flags whatever mix of them the ranks run)
-            if (P.xch.world > 1 && (long long)qb * kBlockM < P.nq) k = exchange_and_merge(P.xch, row, has_row, k, qb);
-            if (has_row) {
-                *reinterpret_cast<ulonglong2*>(P.final_out + ((long long)b * P.nq + row) * 2) = k;
-                select_candidate(P.sel, b, k);
+        if (kWorker && my_row >= 0 && my_row < rows_present()) {
+            if constexpr (C::kColSplit == 2) {     // fold the upper column half's candidates (u64 min = cv2's order)
+                const ulonglong2 o = handover[my_row_in_cta];
+                top2_insert(my_keys.x, my_keys.y, o.x);
+                top2_insert(my_keys.x, my_keys.y, o.y);
+            }
+            unsigned long long* out = P.out + (long long)split * P.out_split_stride + ((long long)b * P.nq + my_row) * 2;
+            *reinterpret_cast<ulonglong2*>(out) = my_keys;
+            if (!P.counters) select_candidate(P.sel, b, my_keys);      // unsplit launch: these are the row's final keys
+        }
+        // ---- in-kernel merge of the train splits: the last CTA of this query block folds all partials ----
+        if (P.counters) {
+            int* flag = reinterpret_cast<int*>(tmem_base_slot + 1);
+            if (last_cta_arrives(&P.counters[(long long)b * gridDim.x + qb], (unsigned)P.splits, flag)) {
+                const long long row = (long long)qb * kBlockM + threadIdx.x;
+                const bool has_row = kWorker && threadIdx.x < kBlockM && row < rows_present();
+                ulonglong2 k = make_ulonglong2(kNoMatch, kNoMatch);
+                if (has_row) fold_partials(P.out, P.splits, P.out_split_stride, (long long)b * P.nq + row, k.x, k.y);
+                // sharded database: push to the peer GPUs, wait for theirs, merge -- still inside this launch
+                // (only query blocks that hold rows take part: hm_exchange_merge_kernel on a peer covers exactly
+                // ceil(nq / 256) blocks, so both kernels post and wait on the same flags whatever mix of them the ranks run)
+                if (P.xch.world > 1 && (long long)qb * kBlockM < P.nq) k = exchange_and_merge(P.xch, row, has_row, k, qb);
+                if (has_row) {
+                    *reinterpret_cast<ulonglong2*>(P.final_out + ((long long)b * P.nq + row) * 2) = k;
+                    select_candidate(P.sel, b, k);
+                }
             }
         }
-    }
-    if (threadIdx.x == 0) cta_mark(P, 4);
-    if (threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && P.clock_probe) {
-        unsigned long long t;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-        P.clock_probe[2] = (long long)t;
-        P.clock_probe[3] = clock64();
+        if (kWorker && threadIdx.x == 0) cta_mark(P, 4);
+        if (kWorker && threadIdx.x == 0 && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && P.clock_probe) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            P.clock_probe[2] = (long long)t;
+            P.clock_probe[3] = clock64();
+        }
+    };
+
+    if constexpr (C::kRegisterHandover) {
+        // Register handover: the control warpgroup (producer, issuer, two idle warps) drops to 32 registers and never
+        // comes back -- its whole remaining path, tail included, is compiled under that budget -- and the epilogue
+        // warps rise to 112 (4 x 32 + 16 x 112 = 20 x 96, the registers the CTA was launched with).
+        if (warp >= kProducerWarp) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
+            if (warp == kProducerWarp) run_producer();
+            else if (warp == kIssuerWarp) run_issuer();
+            run_tail(std::false_type{});
+            return;
+        }
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
+        run_epilogue();
+        run_tail(std::true_type{});
+    } else {
+        if (warp == kProducerWarp) run_producer();
+        else if (warp == kIssuerWarp) run_issuer();
+        else run_epilogue();
+        run_tail(std::true_type{});
     }
 }
 

@@ -64,6 +64,34 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
     return ok != 0;
 }
 // non-blocking probe (never suspends the thread)
+// the same on a precomputed shared-memory address
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar_addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar_addr)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar_addr) : "memory");
+}
+// A shared-memory word read back through a volatile load: the value is opaque to ptxas, so addresses derived from it
+// stay in a register instead of being recomputed (S2R + address arithmetic) inside a hot loop.
+__device__ __forceinline__ uint32_t lds_volatile_u32(uint32_t addr)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.shared.u32 %0, [%1];\n" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity)
 {
     uint32_t ok;
