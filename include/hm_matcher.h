@@ -45,7 +45,7 @@ extern "C" {
 #define HM_API __attribute__((visibility("default")))
 #endif
 
-#define HM_ABI_VERSION 3
+#define HM_ABI_VERSION 4
 #define HM_DESC_BYTES 32
 #define HM_DESC_BITS 256
 #define HM_NO_MATCH 0xFFFFFFFFFFFFFFFFull
@@ -272,6 +272,34 @@ HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
  * calls on the context are ordered after it. */
 HM_API int hm_frame_put(hm_context* ctx, int slot, const uint8_t* desc_host, int64_t n, int64_t stride,
                         const int32_t* points_host);
+/* ---- ORB descriptor stage on the device: replaces the descriptor half of
+ *      /root/reference/feature_detectors.py:25-26 (cv2.ORB.detectAndCompute), called from
+ *      /root/reference/frontend.py:245-249.  Keypoint DETECTION stays with cv2 on the host; what runs here is what
+ *      cv2 does after it: gray conversion, the 1.2^level scale pyramid (bit-exact bilinear, each level from the
+ *      previous one), the 32-pixel reflect-101 frame, the 7 x 7 sigma-2 blur and the 256 rotated rBRIEF comparisons
+ *      (oracle/orb_oracle.py states every step; results are bit-identical to cv2 4.13 for the same keypoints). */
+#define HM_ORB_MAX_LEVELS 16
+#define HM_ORB_BORDER 32
+HM_API size_t hm_orb_workspace_bytes(int rows, int cols, int n_levels);
+/* size and 1 / scale of pyramid level `level` (host arithmetic, no device needed) */
+HM_API int hm_orb_level_geometry(int rows, int cols, int level, int* out_rows, int* out_cols, float* out_inv_scale);
+/* (cos, sin) pairs of keypoint angles in degrees, with the arithmetic cv2 uses: float radians, double cos / sin, rounded to float (host) */
+HM_API int hm_orb_angles_to_cs(const float* angle_deg_host, int64_t n, float* cs_host);
+/* image: device uint8, 1 (gray) or 3 (BGR) channels, rows `row_stride` bytes apart -> blurred pyramid in `workspace` */
+HM_API int hm_orb_build_pyramid(const uint8_t* image, int rows, int cols, int64_t row_stride, int channels, int n_levels,
+                                void* workspace, size_t workspace_bytes, void* stream);
+/* n keypoints: kp_xy = KeyPoint.pt (level-0 pixels, float pairs, 8-byte aligned), kp_cs = hm_orb_angles_to_cs of
+ * KeyPoint.angle, kp_octave = KeyPoint.octave (< n_levels) -> out_desc[n] rows of 32 bytes, `out_stride` bytes apart.
+ * `workspace` is the one hm_orb_build_pyramid filled for the same (rows, cols, n_levels). */
+HM_API int hm_orb_describe(const void* workspace, int rows, int cols, int n_levels, const float* kp_xy, const float* kp_cs,
+                           const int32_t* kp_octave, int64_t n, uint8_t* out_desc, int64_t out_stride, void* stream);
+/* Host image + keypoints -> descriptors written straight into frame slot `slot` (they never visit the host unless
+ * out_desc_host is non-NULL); points_host as in hm_frame_put.  One H2D, the kernels above, no synchronisation unless
+ * a copy is requested. */
+HM_API int hm_frame_put_orb(hm_context* ctx, int slot, const uint8_t* image_host, int rows, int cols, int64_t row_stride,
+                            int channels, int n_levels, const float* kp_xy_host, const float* kp_angle_deg_host,
+                            const int32_t* kp_octave_host, int64_t n, const int32_t* points_host, uint8_t* out_desc_host);
+
 /* hm_match_host between two resident frames (query = current frame, train = last frame).  Outputs as
  * hm_match_host; out_q/out_t/out_d may be NULL.  When both out_*_pts_host are non-NULL (each [nq][2] int32)
  * they receive the matched keypoint positions, gathered on the device: [m] = position of the query / train

@@ -5,6 +5,7 @@ The package holds only what the hot path needs: ``csrc/`` (hand-written sm_100a 
 kernels and the C ABI of ``include/hm_matcher.h``), the ctypes binding, and the host-side
 mirror of the reference's plugin interface.
 """
+from .feature_detectors import FeatureDetector, OrbFeatureDetector
 from .feature_matchers import (BFMatcher, BruteForceFeatureMatcher, DMatch, FeatureMatcher,
                                MatcherError, NORM_HAMMING)
 from .frontend_glue import (FrameDescriptorStore, get_descriptors, get_featured_detection_mask, keypoint_array,
@@ -12,6 +13,6 @@ from .frontend_glue import (FrameDescriptorStore, get_descriptors, get_featured_
 from .keyframe_db import ShardedKeyframeDatabase, shard_ranges
 from ._native import NativeError
 
-__all__ = ["FrameDescriptorStore", "get_descriptors", "get_featured_detection_mask", "keypoint_array", "match_features", "matched_point_arrays",
+__all__ = ["FeatureDetector", "OrbFeatureDetector", "FrameDescriptorStore", "get_descriptors", "get_featured_detection_mask", "keypoint_array", "match_features", "matched_point_arrays",
            "propagate_map_points", "BFMatcher", "BruteForceFeatureMatcher", "DMatch", "FeatureMatcher", "MatcherError",
            "NORM_HAMMING", "NativeError", "ShardedKeyframeDatabase", "shard_ranges"]

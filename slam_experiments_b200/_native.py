@@ -38,6 +38,8 @@ EXPORTS = (
     "hm_merge_top2", "hm_exchange_bytes", "hm_exchange_merge", "hm_filter_matches", "hm_match_fused", "hm_gather_points", "hm_rasterize_mask",
     "hm_context_create", "hm_context_destroy", "hm_knn2_host", "hm_match_host", "hm_frame_put", "hm_frame_match",
     "hm_resident_query_begin", "hm_resident_query_end",
+    "hm_orb_workspace_bytes", "hm_orb_level_geometry", "hm_orb_angles_to_cs", "hm_orb_build_pyramid", "hm_orb_describe",
+    "hm_frame_put_orb",
 )
 
 
@@ -117,6 +119,18 @@ def _declare(L):
     L.hm_frame_match.argtypes = [vp, ci, ci, cu, vp, c.c_double, ci, vp, vp, vp, vp, vp, vp]
     L.hm_match_host.restype = ci
     L.hm_match_host.argtypes = [vp, vp, i64, i64, vp, i64, i64, cu, vp, c.c_double, ci, vp, vp, vp, vp]
+    L.hm_orb_workspace_bytes.restype = sz
+    L.hm_orb_workspace_bytes.argtypes = [ci, ci, ci]
+    L.hm_orb_level_geometry.restype = ci
+    L.hm_orb_level_geometry.argtypes = [ci, ci, ci, c.POINTER(ci), c.POINTER(ci), c.POINTER(c.c_float)]
+    L.hm_orb_angles_to_cs.restype = ci
+    L.hm_orb_angles_to_cs.argtypes = [vp, i64, vp]
+    L.hm_orb_build_pyramid.restype = ci
+    L.hm_orb_build_pyramid.argtypes = [vp, ci, ci, i64, ci, ci, vp, sz, vp]
+    L.hm_orb_describe.restype = ci
+    L.hm_orb_describe.argtypes = [vp, ci, ci, ci, vp, vp, vp, i64, vp, i64, vp]
+    L.hm_frame_put_orb.restype = ci
+    L.hm_frame_put_orb.argtypes = [vp, ci, vp, ci, ci, i64, ci, ci, vp, vp, vp, i64, vp, vp]
 
 
 def lib():
@@ -518,6 +532,62 @@ def rasterize_mask(points: torch.Tensor, shape, radius: int, inner: bool = True,
     return out
 
 
+# ---- ORB descriptor stage (hm_orb.cu) --------------------------------------------------------------------
+def orb_level_geometry(rows: int, cols: int, level: int):
+    """``(rows, cols, 1 / scale)`` of pyramid level ``level`` -- host arithmetic, no device needed."""
+    r, c_, inv = ctypes.c_int(), ctypes.c_int(), ctypes.c_float()
+    check(lib().hm_orb_level_geometry(int(rows), int(cols), int(level), ctypes.byref(r), ctypes.byref(c_), ctypes.byref(inv)),
+          "hm_orb_level_geometry")
+    return r.value, c_.value, inv.value
+
+
+def orb_angles_to_cs(angles_deg: np.ndarray) -> np.ndarray:
+    """``[n, 2] float32`` (cos, sin) of keypoint angles in degrees, computed the way cv2 computes them."""
+    a = np.ascontiguousarray(angles_deg, dtype=np.float32).reshape(-1)
+    out = np.empty((a.shape[0], 2), np.float32)
+    check(lib().hm_orb_angles_to_cs(a.ctypes.data if a.shape[0] else None, a.shape[0], out.ctypes.data if a.shape[0] else None),
+          "hm_orb_angles_to_cs")
+    return out
+
+
+def orb_build_pyramid(image: torch.Tensor, n_levels: int = 8, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``hm_orb_build_pyramid``: CUDA uint8 image ``[h, w]`` (gray) or ``[h, w, 3]`` (BGR) -> the workspace tensor that
+    holds the framed, blurred scale pyramid (input of :func:`orb_describe`)."""
+    if image.dtype != torch.uint8 or not image.is_cuda or image.dim() not in (2, 3) or (image.dim() == 3 and image.shape[2] != 3):
+        raise ValueError("image must be a CUDA uint8 tensor [h, w] or [h, w, 3]")
+    if image.stride(-1) != 1 or (image.dim() == 3 and image.stride(1) != 3):
+        image = image.contiguous()
+    h, w, ch = int(image.shape[0]), int(image.shape[1]), (3 if image.dim() == 3 else 1)
+    need = lib().hm_orb_workspace_bytes(h, w, int(n_levels))
+    if not need:
+        raise NativeError(f"hm_orb_workspace_bytes failed: {last_error()}")
+    dev = image.device
+    if workspace is None or workspace.numel() < need:
+        workspace = torch.empty(need, dtype=torch.uint8, device=dev)
+    with on_device(dev):
+        check(lib().hm_orb_build_pyramid(image.data_ptr(), h, w, image.stride(0), ch, int(n_levels), workspace.data_ptr(),
+                                         workspace.numel(), _stream_ptr(dev)), "hm_orb_build_pyramid")
+    return workspace
+
+
+def orb_describe(workspace: torch.Tensor, shape, n_levels: int, xy: torch.Tensor, cs: torch.Tensor, octave: torch.Tensor,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``hm_orb_describe``: ``[n, 32] uint8`` rBRIEF descriptors of ``n`` keypoints (``xy`` / ``cs`` float32 ``[n, 2]``,
+    ``octave`` int32 ``[n]``, all contiguous CUDA tensors) from a pyramid built for an image of ``shape``."""
+    n = int(xy.shape[0])
+    dev = workspace.device
+    for t, dt in ((xy, torch.float32), (cs, torch.float32), (octave, torch.int32)):
+        if t.dtype != dt or not t.is_cuda or not t.is_contiguous() or t.shape[0] != n:
+            raise ValueError("xy / cs must be contiguous CUDA float32 [n, 2], octave int32 [n]")
+    if out is None:
+        out = torch.empty((n, DESC_BYTES), dtype=torch.uint8, device=dev)
+    with on_device(dev):
+        check(lib().hm_orb_describe(workspace.data_ptr(), int(shape[0]), int(shape[1]), int(n_levels), xy.data_ptr(), cs.data_ptr(),
+                                    octave.data_ptr(), n, out.data_ptr(), out.stride(0) if n else DESC_BYTES, _stream_ptr(dev)),
+              "hm_orb_describe")
+    return out
+
+
 def profile_events(start: Optional[torch.cuda.Event], stop: Optional[torch.cuda.Event]) -> None:
     """``hm_profile_events``: record ``start``/``stop`` around the dominant kernel of later calls
     made from this thread (events must have been created with ``enable_timing=True``)."""
@@ -654,6 +724,32 @@ class HostContext:
             p_ptr = positions.ctypes.data
         check(lib().hm_frame_put(self._h, slot, d.ctypes.data if d.shape[0] else None, d.shape[0],
                                  d.strides[0] if d.shape[0] else DESC_BYTES, p_ptr), "hm_frame_put")
+
+    def frame_put_orb(self, slot: int, image: np.ndarray, xy: np.ndarray, angles_deg: np.ndarray, octaves: np.ndarray,
+                      n_levels: int = 8, positions: Optional[np.ndarray] = None, want_descriptors: bool = False):
+        """``hm_frame_put_orb``: the frame's descriptors are computed on the device from the image and cv2's keypoints and
+        stored in ``slot``; returns them as ``[n, 32] uint8`` only when ``want_descriptors``."""
+        img = image
+        if img.dtype != np.uint8 or img.ndim not in (2, 3) or (img.ndim == 3 and img.shape[2] != 3):
+            raise ValueError("image must be uint8 [h, w] or [h, w, 3]")
+        if img.strides[-1] != 1 or (img.ndim == 3 and img.strides[1] != 3) or img.strides[0] < img.shape[1] * (3 if img.ndim == 3 else 1):
+            img = np.ascontiguousarray(img)
+        xy = np.ascontiguousarray(xy, dtype=np.float32).reshape(-1, 2)
+        ang = np.ascontiguousarray(angles_deg, dtype=np.float32).reshape(-1)
+        octv = np.ascontiguousarray(octaves, dtype=np.int32).reshape(-1)
+        n = xy.shape[0]
+        if ang.shape[0] != n or octv.shape[0] != n:
+            raise ValueError("xy, angles and octaves must have one entry per keypoint")
+        p_ptr = None
+        if positions is not None:
+            positions = np.ascontiguousarray(positions, dtype=np.int32)
+            p_ptr = positions.ctypes.data
+        out = np.empty((n, DESC_BYTES), np.uint8) if want_descriptors else None
+        check(lib().hm_frame_put_orb(self._h, slot, img.ctypes.data, img.shape[0], img.shape[1], img.strides[0],
+                                     3 if img.ndim == 3 else 1, int(n_levels), xy.ctypes.data if n else None,
+                                     ang.ctypes.data if n else None, octv.ctypes.data if n else None, n, p_ptr,
+                                     out.ctypes.data if (want_descriptors and n) else None), "hm_frame_put_orb")
+        return out
 
     def frame_match(self, train_slot: int, query_slot: int, nq: int, ratio: Optional[float] = None,
                     cross_check: bool = False, dist_threshold: Optional[float] = None, variant="auto",

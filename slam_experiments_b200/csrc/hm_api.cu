@@ -671,6 +671,7 @@ struct hm_context {
     uint8_t* h_buf;      // pinned staging, same carving for query | train | keys
     size_t h_cap;
     FrameSlot slots[kFrameSlots];   // resident frames (hm_frame_put / hm_frame_match)
+    cudaEvent_t staged;             // the last unsynchronised H2D out of h_buf (hm_frame_put_orb)
 };
 
 HM_API int hm_context_create(hm_context** out_ctx)
@@ -710,6 +711,7 @@ HM_API void hm_context_destroy(hm_context* ctx)
     }
     if (ctx->d_buf) cudaFree(ctx->d_buf);
     if (ctx->h_buf) cudaFreeHost(ctx->h_buf);
+    if (ctx->staged) cudaEventDestroy(ctx->staged);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -821,6 +823,7 @@ HM_API int hm_knn2_host(hm_context* ctx, const uint8_t* query_host, int64_t nq, 
 
 static int ctx_reserve(hm_context* ctx, size_t dneed, size_t hneed)
 {
+    if (ctx->d_cap < dneed || ctx->h_cap < hneed) HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // queued work may still use the old buffers
     if (ctx->d_cap < dneed) {
         if (ctx->d_buf) cudaFree(ctx->d_buf);
         ctx->d_buf = nullptr; ctx->d_cap = 0;
@@ -985,6 +988,83 @@ HM_API int hm_frame_put(hm_context* ctx, int slot, const uint8_t* desc_host, int
     HM_CUDA_CHECK(cudaEventRecord(f.uploaded, ctx->stream));
     f.n = n;
     f.has_points = points_host != nullptr;
+    return HM_OK;
+}
+
+// Descriptors computed on the device, straight into a frame slot: the image and the keypoints
+// cv2's detector found go up, the pyramid / blur / rBRIEF kernels of hm_orb.cu write the slot's descriptor rows, and
+// nothing comes back unless out_desc_host asks for a copy.  Replaces the descriptor half of
+// /root/reference/feature_detectors.py:25-26 (cv2.ORB.detectAndCompute) + the hm_frame_put upload.
+HM_API int hm_frame_put_orb(hm_context* ctx, int slot, const uint8_t* image_host, int rows, int cols, int64_t row_stride,
+                            int channels, int n_levels, const float* kp_xy_host, const float* kp_angle_deg_host,
+                            const int32_t* kp_octave_host, int64_t n, const int32_t* points_host, uint8_t* out_desc_host)
+{
+    if (!ctx || slot < 0 || slot >= kFrameSlots || n < 0 || !image_host || (channels != 1 && channels != 3) ||
+        row_stride < (int64_t)cols * channels || (n > 0 && (!kp_xy_host || !kp_angle_deg_host || !kp_octave_host))) {
+        set_error("hm_frame_put_orb: bad arguments (slots 0..%d, uint8 image with 1 or 3 channels)", kFrameSlots - 1);
+        return HM_ERR_INVALID_ARGUMENT;
+    }
+    const size_t orb_ws = orb_workspace_bytes(rows, cols, n_levels);
+    if (!orb_ws) return HM_ERR_INVALID_ARGUMENT;                     // orb_geometry set the error
+    for (int64_t i = 0; i < n; ++i)
+        if (kp_octave_host[i] < 0 || kp_octave_host[i] >= n_levels) {
+            set_error("hm_frame_put_orb: keypoint %lld has octave %d, pyramid has %d levels", (long long)i, kp_octave_host[i], n_levels);
+            return HM_ERR_INVALID_ARGUMENT;
+        }
+    FrameSlot& f = ctx->slots[slot];
+    f.n = 0;
+    f.has_points = points_host != nullptr;
+    if (n == 0) return HM_OK;
+    f.has_points = false;
+    // staging / scratch: [image | xy | cs | octave] then the pyramid workspace (device only)
+    const size_t img_b = align_up((size_t)rows * cols * channels, 256), f2_b = align_up((size_t)n * 8, 256), oct_b = align_up((size_t)n * 4, 256);
+    const size_t in_b = img_b + 2 * f2_b + oct_b;
+    if (ctx->staged) HM_CUDA_CHECK(cudaEventSynchronize(ctx->staged));   // the previous put has left the staging buffer
+    int rc = ctx_reserve(ctx, in_b + orb_ws, in_b);
+    if (rc != HM_OK) return rc;
+    const size_t bytes = slot_points_offset(n) + (size_t)n * 8;
+    if (f.cap < bytes) {
+        HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        if (f.d) cudaFree(f.d);
+        if (f.h) cudaFreeHost(f.h);
+        f.d = f.h = nullptr; f.cap = f.h_cap = 0;
+        HM_CUDA_CHECK(cudaMalloc(&f.d, bytes + bytes / 2));
+        if (cudaMallocHost(&f.h, bytes + bytes / 2) != cudaSuccess) {
+            cudaGetLastError();
+            cudaFree(f.d);
+            f.d = f.h = nullptr;
+            set_error("hm_frame_put_orb: cudaMallocHost(%zu) failed", bytes + bytes / 2);
+            return HM_ERR_CUDA;
+        }
+        f.cap = f.h_cap = bytes + bytes / 2;
+    }
+    if (!f.uploaded) HM_CUDA_CHECK(cudaEventCreateWithFlags(&f.uploaded, cudaEventDisableTiming));
+    else HM_CUDA_CHECK(cudaEventSynchronize(f.uploaded));
+    if (!ctx->staged) HM_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->staged, cudaEventDisableTiming));
+    uint8_t* h = ctx->h_buf;
+    for (int r = 0; r < rows; ++r) memcpy(h + (size_t)r * cols * channels, image_host + (size_t)r * row_stride, (size_t)cols * channels);
+    memcpy(h + img_b, kp_xy_host, (size_t)n * 8);
+    orb_angles_to_cs(kp_angle_deg_host, n, reinterpret_cast<float*>(h + img_b + f2_b));
+    memcpy(h + img_b + 2 * f2_b, kp_octave_host, (size_t)n * 4);
+    uint8_t* d = ctx->d_buf;
+    HM_CUDA_CHECK(cudaMemcpyAsync(d, h, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    HM_CUDA_CHECK(cudaEventRecord(ctx->staged, ctx->stream));
+    if ((rc = launch_orb_pyramid(d, rows, cols, (long long)cols * channels, channels, n_levels, d + in_b, orb_ws, ctx->stream)) != HM_OK) return rc;
+    if ((rc = launch_orb_describe(d + in_b, rows, cols, n_levels, reinterpret_cast<const float*>(d + img_b),
+                                  reinterpret_cast<const float*>(d + img_b + f2_b), reinterpret_cast<const int*>(d + img_b + 2 * f2_b), n,
+                                  f.d, HM_DESC_BYTES, ctx->stream)) != HM_OK) return rc;
+    if (points_host) {
+        memcpy(f.h + slot_points_offset(n), points_host, (size_t)n * 8);
+        HM_CUDA_CHECK(cudaMemcpyAsync(f.d + slot_points_offset(n), f.h + slot_points_offset(n), (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    if (out_desc_host) HM_CUDA_CHECK(cudaMemcpyAsync(f.h, f.d, (size_t)n * HM_DESC_BYTES, cudaMemcpyDeviceToHost, ctx->stream));
+    HM_CUDA_CHECK(cudaEventRecord(f.uploaded, ctx->stream));
+    f.n = n;
+    f.has_points = points_host != nullptr;
+    if (out_desc_host) {
+        HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+        memcpy(out_desc_host, f.h, (size_t)n * HM_DESC_BYTES);
+    }
     return HM_OK;
 }
 

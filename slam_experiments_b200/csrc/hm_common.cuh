@@ -283,6 +283,14 @@ int launch_gather_points(const int* q_idx, const int* t_idx, const int* count, l
                          const int* query_pts, long long nq, const int* train_pts, long long nt, int* out_query,
                          int* out_train, cudaStream_t stream);
 
+// ORB descriptor stage (hm_orb.cu)
+size_t orb_workspace_bytes(int rows, int cols, int n_levels);
+int launch_orb_pyramid(const uint8_t* image, int rows, int cols, long long row_stride, int channels, int n_levels, void* ws,
+                       size_t ws_bytes, cudaStream_t stream);
+int launch_orb_describe(const void* ws, int rows, int cols, int n_levels, const float* xy, const float* cs, const int* octave,
+                        long long n, uint8_t* out, long long out_stride, cudaStream_t stream);
+void orb_angles_to_cs(const float* angle_deg, long long n, float* cs);
+
 int launch_rasterize_mask(const int* pts, long long n, int radius, int inner, unsigned char* mask, int h, int w,
                           long long row_stride, cudaStream_t stream);
 

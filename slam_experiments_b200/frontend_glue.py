@@ -155,6 +155,35 @@ class FrameDescriptorStore:
             del self._frames[frame_id]
             self._points.pop(frame_id, None)
 
+    def put_image(self, frame_id, image: np.ndarray, keypoints, n_levels: int = 8, with_positions: bool = True,
+                  want_descriptors: bool = False):
+        """Store a frame from its IMAGE and cv2 keypoints: the ORB descriptors are computed on the device
+        (``hm_frame_put_orb``) and written into the frame's slot without visiting the host.
+        Returns the descriptors only when ``want_descriptors``."""
+        from .feature_detectors import keypoint_arrays
+        if self._ctx is None:
+            with nat.on_device(self.device):
+                self._ctx = nat.HostContext()
+        xy, ang, octv = keypoint_arrays(keypoints)
+        pos = xy.astype(np.int32) if with_positions else None      # Feature.position: int() of the keypoint coordinates
+        if frame_id in self._slots:
+            slot = self._slots.pop(frame_id)[0]
+        elif self._free_slots:
+            slot = self._free_slots.pop()
+        else:
+            _, (slot, _, _) = self._slots.popitem(last=False)
+        try:
+            with nat.on_device(self.device):
+                out = self._ctx.frame_put_orb(slot, image, xy, ang, octv, n_levels, pos, want_descriptors)
+        except Exception:
+            self._free_slots.append(slot)
+            raise
+        self._slots[frame_id] = (slot, xy.shape[0], pos is not None)
+        if frame_id in self._frames:
+            del self._frames[frame_id]
+            self._points.pop(frame_id, None)
+        return out
+
     def put(self, frame_id, descriptors, positions=None) -> torch.Tensor:
         """Upload a frame once.  ``positions`` (optional ``[N, 2]`` pixel coordinates, truncated to int32 like
         ``Feature.position``) stay resident too, so that :meth:`matched_points` can gather on the device."""

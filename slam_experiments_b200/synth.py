@@ -81,3 +81,25 @@ def euroc_shaped_sequence() -> np.ndarray:
                         "c2_sequence_orb2000.npz")
     with np.load(path) as z:
         return np.ascontiguousarray(z["descriptors"])
+
+
+def textured_image(h: int = 480, w: int = 640, seed: int = 7, channels: int = 1) -> np.ndarray:
+    """A seeded corner-rich test image for the ORB descriptor stage (8f rank 3): smooth random texture (low-resolution
+    noise, bilinearly upsampled) with filled rectangles of random gray levels on top.  cv2's ORB finds several thousand
+    keypoints on all 8 pyramid levels.  uint8 ``[h, w]`` or ``[h, w, 3]`` (BGR planes with different textures)."""
+    rng = np.random.default_rng(seed)
+    planes = []
+    for _ in range(channels):
+        gh, gw = h // 6 + 2, w // 6 + 2
+        g = rng.integers(0, 256, (gh, gw)).astype(np.float64)
+        ys, xs = np.arange(h) / 6.0, np.arange(w) / 6.0
+        y0, x0 = ys.astype(int), xs.astype(int)
+        fy, fx = (ys - y0)[:, None], (xs - x0)[None, :]
+        img = (g[y0][:, x0] * (1 - fy) * (1 - fx) + g[y0][:, x0 + 1] * (1 - fy) * fx +
+               g[y0 + 1][:, x0] * fy * (1 - fx) + g[y0 + 1][:, x0 + 1] * fy * fx)
+        img = np.rint(img).astype(np.uint8)
+        for _ in range(h * w // 5000):
+            y, x = int(rng.integers(0, h - 8)), int(rng.integers(0, w - 8))
+            img[y:y + int(rng.integers(6, 40)), x:x + int(rng.integers(6, 40))] = int(rng.integers(0, 256))
+        planes.append(img)
+    return planes[0] if channels == 1 else np.ascontiguousarray(np.stack(planes, axis=2))

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_version_and_sizing(lib):
-    assert lib.hm_version() == 3
+    assert lib.hm_version() == 4
     I8, F4 = nat.VARIANT_I8, nat.VARIANT_F4
     assert lib.hm_prepared_bytes(0, I8) == 0
     assert lib.hm_prepared_bytes(1, I8) == 256 * 256        # padded to whole 256-row tiles
