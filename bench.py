@@ -513,6 +513,12 @@ def run_b200(args):
                 raise
             except Exception as e:       # anything else is reported, not hidden
                 subs[key] = {"error": f"{type(e).__name__}: {e}"}
+        try:
+            subs["orb_describe"] = bench_extra.measure_orb(sub_steps)
+        except SystemExit:
+            raise
+        except Exception as e:
+            subs["orb_describe"] = {"error": f"{type(e).__name__}: {e}"}
         line["configs"] = subs
 
     # ---- cpu baseline beside it (rank 0, N=1 only): cv2 on the host cores, bounded sample ----------------

@@ -101,10 +101,10 @@ HM_API int hm_describe_launch(int64_t nq, int64_t nt, int batch, int variant, ch
 HM_API size_t hm_workspace_bytes(int64_t nq, int64_t nt, int batch, int variant);
 
 /* ---- measurement hook ---------------------------------------------------------------- */
-/* When both are non-NULL (cudaEvent_t as void*), every later k-NN call of this thread records
- * `start` immediately before and `stop` immediately after the launch of its dominant kernel
- * (hm_popc_knn2_kernel, hm_i8_knn2_kernel or hm_f4_knn2_kernel) on the call's stream, so bench.py can time that
- * kernel alone with CUDA events.  Pass NULLs to switch it off.  Not part of the data path. */
+/* When both are non-NULL (cudaEvent_t as void*), the NEXT dominant-kernel launch of this thread
+ * (hm_popc_knn2_kernel, hm_i8_knn2*_kernel or hm_f4_knn2*_kernel: the forward k-NN of a pipeline call) records
+ * `start` immediately before and `stop` immediately after it on the call's stream, so bench.py can time that
+ * kernel alone with CUDA events; call again to re-arm.  Pass NULLs to switch it off.  Not part of the data path. */
 HM_API void hm_profile_events(void* start_event, void* stop_event);
 
 /* ---- k-NN core: replaces cv2.BFMatcher.knnMatch(query, train, k=2) and, through key[0],

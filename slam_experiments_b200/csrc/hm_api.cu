@@ -24,11 +24,15 @@ void set_error(const char* fmt, ...)
 }
 
 static thread_local cudaEvent_t g_prof_start = nullptr, g_prof_stop = nullptr;
+static thread_local bool g_prof_armed = false;
 
+// The event pair brackets the FIRST dominant-kernel launch after hm_profile_events() armed it: the forward k-NN of a
+// pipeline call (its swapped / candidate pass is not the kernel the roofline line is about).
 void profile_mark(bool start, cudaStream_t stream)
 {
-    cudaEvent_t e = start ? g_prof_start : g_prof_stop;
-    if (g_prof_start && g_prof_stop) cudaEventRecord(e, stream);
+    if (!g_prof_armed || !g_prof_start || !g_prof_stop) return;
+    cudaEventRecord(start ? g_prof_start : g_prof_stop, stream);
+    if (!start) g_prof_armed = false;
 }
 
 int device_info(DeviceInfo* out)
@@ -199,6 +203,7 @@ HM_API void hm_profile_events(void* start_event, void* stop_event)
 {
     g_prof_start = static_cast<cudaEvent_t>(start_event);
     g_prof_stop = static_cast<cudaEvent_t>(stop_event);
+    g_prof_armed = start_event && stop_event;
 }
 
 HM_API int hm_device_sm_count(void)

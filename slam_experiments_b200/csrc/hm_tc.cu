@@ -1120,6 +1120,18 @@ int resident_ctas(int cs, int sm_count)
     return v;
 }
 
+// fixed per-CTA cost in steady-state tile times (HM_PROLOGUE_TILES overrides, for planner sweeps)
+template <class C>
+int prologue_tiles()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HM_PROLOGUE_TILES");
+        v = e ? atoi(e) : C::kPrologueTiles;
+    }
+    return v;
+}
+
 template <class C>
 TcPlan plan_tc(long long nq, long long nt, int batch, int sm_count)
 {
@@ -1141,7 +1153,7 @@ TcPlan plan_tc(long long nq, long long nt, int batch, int sm_count)
         const long long tps = ceil_div(pl.ntiles, s);
         const long long real_s = ceil_div(pl.ntiles, tps);
         const long long waves = ceil_div(items * real_s, sm_count);
-        const long long cost = waves * (tps + C::kPrologueTiles);
+        const long long cost = waves * (tps + prologue_tiles<C>());
         if (best_cost < 0 || cost < best_cost) {
             best_cost = cost;
             best = s;
