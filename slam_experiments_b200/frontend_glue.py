@@ -268,3 +268,75 @@ class FrameDescriptorStore:
         if dist_threshold and len(matches) != 0:
             return matches
         return tuple(matches)
+
+
+class KeyframeWindow:
+    """A local window of keyframes resident in ONE device buffer, matched against the current frame in one batched
+    call (BASELINE config C5: 32 train frames x 10,000 rows, ratio test + mutual check).
+
+    The reference keeps its active keyframes in the backend's map (`/root/reference/backend.py:11`, 7 of them) and
+    would match them one ``match()`` call at a time, re-packing and re-sending both sides each time
+    (`frontend.py:181-187`).  Here ``put(i, descriptors)`` uploads a keyframe once into ring position ``i``;
+    ``match(query)`` sends only the current frame's descriptors (or one query per keyframe), runs ONE fused pipeline
+    launch over all resident frames -- forward k-NN with the ratio test inside, candidate pass of the mutual check,
+    filter -- and brings every match list back with one D2H.  All frames of a window share one row count (the batched
+    kernels take one shape per launch; ORB returns exactly ``n_features`` on ordinary content)."""
+
+    def __init__(self, capacity: int = 32, *, ratio: Optional[float] = None, cross_check: bool = False, device=None,
+                 variant: str = "auto"):
+        self.device = nat.require_cuda(device)
+        self.capacity = int(capacity)
+        self.ratio, self.cross_check, self.variant = ratio, bool(cross_check), variant
+        self._buf: Optional[torch.Tensor] = None          # [capacity, rows, 32]
+        self._present = [False] * self.capacity
+        from .feature_matchers import _Staging
+        self._staging = _Staging()
+
+    @property
+    def rows(self) -> int:
+        return 0 if self._buf is None else int(self._buf.shape[1])
+
+    def put(self, index: int, descriptors: np.ndarray) -> None:
+        a = np.asarray(descriptors)
+        if a.dtype != np.uint8 or a.ndim != 2 or a.shape[1] != nat.DESC_BYTES or a.shape[0] == 0:
+            raise MatcherError(f"descriptors: expected non-empty uint8 [N, {nat.DESC_BYTES}], got {a.dtype} {a.shape}")
+        if not 0 <= index < self.capacity:
+            raise MatcherError(f"window index {index} out of range 0..{self.capacity - 1}")
+        with nat.on_device(self.device):
+            if self._buf is None:
+                self._buf = torch.empty((self.capacity, a.shape[0], nat.DESC_BYTES), dtype=torch.uint8, device=self.device)
+            if a.shape[0] != self._buf.shape[1]:
+                raise MatcherError(f"every keyframe of a window has the same row count ({self._buf.shape[1]}), got {a.shape[0]}")
+            self._buf[index].copy_(self._staging.to_device("kf", a, self.device), non_blocking=True)
+        self._present[index] = True
+
+    def match_tensors(self, query: np.ndarray, dist_threshold: Optional[float] = None):
+        """``query``: ``[Nq, 32]`` (the current frame against every resident keyframe) or ``[B, Nq, 32]`` (one query per
+        resident keyframe, in ring order).  Returns a list with one ``(queryIdx, trainIdx, distance)`` triple of int32
+        arrays per resident keyframe, in ring order."""
+        idx = [i for i, p in enumerate(self._present) if p]
+        if not idx:
+            return []
+        q = np.asarray(query)
+        if q.dtype != np.uint8 or q.shape[-1] != nat.DESC_BYTES or q.ndim not in (2, 3) or (q.ndim == 3 and q.shape[0] != len(idx)):
+            raise MatcherError(f"query: expected uint8 [Nq, 32] or [{len(idx)}, Nq, 32], got {q.dtype} {q.shape}")
+        nq = q.shape[-2]
+        if nq == 0:
+            e = np.empty(0, np.int32)
+            return [(e, e.copy(), e.copy()) for _ in idx]
+        with nat.on_device(self.device):
+            train = self._buf if len(idx) == self.capacity else self._buf[torch.tensor(idx, device=self.device)]
+            qd = self._staging.to_device("wq", q.reshape(-1, nat.DESC_BYTES), self.device)
+            qd = qd.view(len(idx), nq, nat.DESC_BYTES) if q.ndim == 3 else qd.unsqueeze(0).expand(len(idx), nq, nat.DESC_BYTES)
+            oq, ot, od, cnt = nat.match_fused(qd, train, ratio=self.ratio, cross_check=self.cross_check,
+                                              dist_threshold=dist_threshold if dist_threshold else None, variant=self.variant)
+            host = self._staging.to_host("wm", torch.cat([cnt.view(-1), oq.view(-1), ot.view(-1), od.view(-1)]))
+        b = len(idx)
+        counts = host[:b]
+        body = host[b:].reshape(3, b, nq)
+        return [(body[0, i, :counts[i]].copy(), body[1, i, :counts[i]].copy(), body[2, i, :counts[i]].copy()) for i in range(b)]
+
+    def match(self, query: np.ndarray, dist_threshold: Optional[float] = None):
+        """DMatch tuples per resident keyframe (``imgIdx`` = ring position)."""
+        idx = [i for i, p in enumerate(self._present) if p]
+        return [tuple(_build_dmatches(q, t, d, i)) for i, (q, t, d) in zip(idx, self.match_tensors(query, dist_threshold))]

@@ -188,3 +188,30 @@ def test_store_accepts_cuda_tensors():
     for x, y in zip(a.matched_points(0, 1), b.matched_points(0, 1)):
         assert np.array_equal(x, y)
     assert [(m.queryIdx, m.trainIdx) for m in a.match(0, 1)] == [(m.queryIdx, m.trainIdx) for m in b.match(0, 1)]
+
+
+@pytest.mark.gpu
+def test_keyframe_window_batched_match_equals_oracle():
+    """C5-shaped local window: resident keyframes, one batched pipeline call, one query for all / one query each."""
+    from oracle import c_oracle as co
+    from slam_experiments_b200 import synth
+    rng = np.random.default_rng(17)
+    kfs = rng.integers(0, 256, (5, 700, 32), dtype=np.uint8)
+    win = sx.KeyframeWindow(capacity=6, ratio=0.8, cross_check=True, variant="f4")
+    for i in (0, 1, 2, 4, 5):
+        win.put(i, kfs[min(i, 4) if i != 5 else 3])
+    order = [0, 1, 2, 4, 3]
+    q1 = synth.matchable_queries(kfs[2], 650, 3)
+    out = win.match_tensors(q1)
+    assert len(out) == 5
+    for (q, t, d), k in zip(out, order):
+        eq, et, ed = co.pipeline(q1, kfs[k], 0.8, True)
+        assert np.array_equal(q, eq) and np.array_equal(t, et) and np.array_equal(d, ed)
+    qs = np.stack([synth.matchable_queries(kfs[k], 300, 40 + k) for k in order])
+    for (q, t, d), k, qq in zip(win.match_tensors(qs), order, qs):
+        eq, et, ed = co.pipeline(qq, kfs[k], 0.8, True)
+        assert np.array_equal(q, eq) and np.array_equal(t, et) and np.array_equal(d, ed)
+    dm = win.match(q1)
+    assert [m.imgIdx for m in dm[2][:1]] == [2] and [len(x) for x in dm] == [len(o[0]) for o in out]
+    with pytest.raises(sx.MatcherError):
+        win.put(3, kfs[0][:10])

@@ -199,6 +199,17 @@ def measure(wl, steps, warmup, variant_arg="auto", n_arg=65536, cpu_seconds=10.0
         def e2e_arr():
             for i in range(nb):
                 m.match_tensors(ts[i], qs[i])
+        # the window resident on the device (KeyframeWindow): only the queries cross PCIe, one batched call, one D2H
+        win = sx.KeyframeWindow(nb, ratio=0.75, cross_check=True, variant=args.variant)
+        for i in range(nb):
+            win.put(i, ts[i])
+        got = win.match_tensors(qs)
+        eq0 = c_oracle.pipeline(qs[5], ts[5], 0.75, True)
+        if not all(np.array_equal(a, b) for a, b in zip(got[5], eq0)):
+            raise SystemExit("bench: KeyframeWindow differs from the oracle")
+        extra_e2e = {"resident_window_arrays_out": lambda: win.match_tensors(qs),
+                     "resident_window_dmatch_out": lambda: win.match(qs),
+                     "resident_window_one_query_arrays_out": lambda: win.match_tensors(qs[0])}
         h2d, d2h = nb * 2 * 10000 * 32, nb * 10000 * 12
         cfg = {"workload": "c5_local_window_32x10k", "pipeline": "knn2 + ratio 0.75 (in the k-NN kernel) + mutual cross-check over the candidate train rows", "variant": variant,
                "pairs_counted": "Nq*Nt*batch (the candidate pass of the mutual check counts no extra pairs)"}
@@ -254,7 +265,7 @@ def measure(wl, steps, warmup, variant_arg="auto", n_arg=65536, cpu_seconds=10.0
 
     reps = max(2, min(steps, 5)) if wl != "c1" else 2000
     e2e_s, e2e_arr_s = wall(e2e_fn, reps), wall(e2e_arr, reps)
-    extra_s = {k: wall(f, reps) for k, f in (extra_e2e if wl == "c2" else {}).items()}
+    extra_s = {k: wall(f, reps) for k, f in (extra_e2e if wl in ("c2", "c5") else {}).items()}
 
     # cpu baseline: bounded sample, about `cpu_seconds`
     unit_probe = 8 if wl == "c3" else 1
@@ -290,4 +301,10 @@ def measure(wl, steps, warmup, variant_arg="auto", n_arg=65536, cpu_seconds=10.0
                                      "cpu": k / dt}
         for name, sec in extra_s.items():
             line["frame_pairs_per_s"]["e2e_" + name] = nb / sec
+    if wl == "c5":      # the same metric through the resident window: train frames stay in HBM, only the queries cross PCIe
+        line["e2e"]["resident_window"] = {
+            name: {"value": pairs / sec / 1e9, "unit": UNIT, "ms_per_step": sec * 1e3,
+                   "h2d_bytes_per_step": (10000 * 32) * (1 if "one_query" in name else nb), "d2h_bytes_per_step": nb * 4 + nb * 10000 * 12}
+            for name, sec in extra_s.items()}
+        line["e2e"]["resident_window"]["api"] = "KeyframeWindow.match_tensors / match: one batched pipeline call over the resident keyframes"
     return line
