@@ -266,6 +266,9 @@ HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
 
 /* ---- resident frames (SURVEY.md 8f ranks 1 + 2): replaces the per-call repacking of
  *      /root/reference/primitives.py:200-205 + frontend.py:181-187 and the point loops of utils.py:13-19 ---- */
+/* problems up to this size take the single-launch path of hm_match_host / hm_frame_match (csrc/hm_small.cu) */
+#define HM_SMALL_MAX_ROWS 1024
+#define HM_SMALL_MAX_PAIRS 262144
 #define HM_FRAME_SLOTS 16
 /* Upload a frame ONCE into `slot` (0 .. HM_FRAME_SLOTS-1) of the context: n descriptors (rows `stride` bytes
  * apart) and, when points_host != NULL, its n keypoint positions (x, y int32 pairs).  Asynchronous; later

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libhm_matcher.so")
-SOURCES = ["hm_api.cu", "hm_popc.cu", "hm_tc.cu", "hm_epilogue.cu", "hm_orb.cu"]
+SOURCES = ["hm_api.cu", "hm_popc.cu", "hm_tc.cu", "hm_epilogue.cu", "hm_orb.cu", "hm_small.cu"]
 HEADERS = ["hm_common.cuh", "hm_tcgen05.cuh", "hm_orb_pattern.inc"]
 
 

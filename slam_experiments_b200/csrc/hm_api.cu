@@ -677,6 +677,7 @@ struct hm_context {
     size_t h_cap;
     FrameSlot slots[kFrameSlots];   // resident frames (hm_frame_put / hm_frame_match)
     cudaEvent_t staged;             // the last unsynchronised H2D out of h_buf (hm_frame_put_orb)
+    unsigned small_epoch;           // call counter of the single-launch small-problem path (hm_small.cu)
 };
 
 HM_API int hm_context_create(hm_context** out_ctx)
@@ -853,6 +854,38 @@ static void copy_rows(uint8_t* dst, const uint8_t* src, int64_t n, int64_t strid
     }
 }
 
+// Single-launch path for small problems (hm_small.cu): the kernel publishes its results and then the call's epoch into
+// mapped pinned memory; the host polls that word instead of synchronising the stream.  `res` = host view of the result
+// block [count, epoch, pad, pad][q][t][d].  Returns HM_OK once the results are visible.
+static int small_match_run(hm_context* ctx, const uint8_t* q_dev, int64_t nq, const uint8_t* t_dev, int64_t nt, unsigned flags,
+                           const RatioLut& lut, int thr, int* res)
+{
+    int* res_dev = nullptr;
+    HM_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&res_dev), res, 0));
+    const unsigned epoch = ++ctx->small_epoch ? ctx->small_epoch : ++ctx->small_epoch;      // never 0
+    volatile int* vres = res;
+    vres[1] = 0;
+    int rc = launch_small_match(q_dev, nq, t_dev, nt, flags, lut, thr, res_dev, epoch, ctx->stream);
+    if (rc != HM_OK) return rc;
+    for (unsigned long long spins = 1;; ++spins) {
+        if ((unsigned)vres[1] == epoch) break;
+        if ((spins & 0x3FFF) == 0) {                  // the failure check: a kernel that died never publishes
+            const cudaError_t e = cudaStreamQuery(ctx->stream);
+            if (e == cudaSuccess) {
+                if ((unsigned)vres[1] == epoch) break;
+                set_error("small-problem kernel finished without publishing its result");
+                return HM_ERR_CUDA;
+            }
+            if (e != cudaErrorNotReady) {
+                set_error("small-problem kernel failed: %s", cudaGetErrorString(e));
+                return HM_ERR_CUDA;
+            }
+        }
+    }
+    __atomic_thread_fence(__ATOMIC_ACQUIRE);
+    return HM_OK;
+}
+
 HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq, int64_t q_stride,
                          const uint8_t* train_host, int64_t nt, int64_t t_stride, unsigned flags,
                          const uint16_t* ratio_lut_host, double dist_threshold, int variant, int32_t* out_q_host,
@@ -874,6 +907,22 @@ HM_API int hm_match_host(hm_context* ctx, const uint8_t* query_host, int64_t nq,
     uint8_t *hq = ctx->h_buf, *ht = hq + qb, *hr = ht + tb;
     copy_rows(hq, query_host, nq, q_stride);
     copy_rows(ht, train_host, nt, t_stride);
+    if (small_match_eligible(nq, nt) && !(g_prof_start && g_prof_stop)) {
+        // one launch, inputs read from the pinned staging buffer, results polled: no copies, no synchronisation
+        RatioLut lut;
+        int thr;
+        if ((rc = build_filter_args(flags, ratio_lut_host, dist_threshold, &lut, &thr)) != HM_OK) return rc;
+        uint8_t* hq_dev = nullptr;
+        HM_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&hq_dev), hq, 0));
+        if ((rc = small_match_run(ctx, hq_dev, nq, hq_dev + qb, nt, flags, lut, thr, reinterpret_cast<int*>(hr))) != HM_OK) return rc;
+        const int32_t n = *reinterpret_cast<int32_t*>(hr);
+        const int32_t* h_q = reinterpret_cast<int32_t*>(hr + 16);
+        memcpy(out_q_host, h_q, (size_t)n * 4);
+        memcpy(out_t_host, h_q + nq, (size_t)n * 4);
+        memcpy(out_d_host, h_q + 2 * nq, (size_t)n * 4);
+        *out_count_host = n;
+        return HM_OK;
+    }
     int32_t* d_count = reinterpret_cast<int32_t*>(dr);
     int32_t* d_q = reinterpret_cast<int32_t*>(dr + 16);
     int32_t* d_t = d_q + nq;
@@ -1106,6 +1155,19 @@ HM_API int hm_frame_match(hm_context* ctx, int train_slot, int query_slot, unsig
     int32_t* d_pq = d_d + nq;          // 16 + 12 nq bytes: 8-byte aligned when nq is even; padded below otherwise
     if (nq & 1) ++d_pq;
     int32_t* d_pt = d_pq + 2 * nq;
+    if (!want_pts && small_match_eligible(nq, nt) && !(g_prof_start && g_prof_stop)) {
+        RatioLut lut;
+        int thr;
+        if ((rc = build_filter_args(flags, ratio_lut_host, dist_threshold, &lut, &thr)) != HM_OK) return rc;
+        if ((rc = small_match_run(ctx, Q.d, nq, T.d, nt, flags, lut, thr, reinterpret_cast<int*>(hr))) != HM_OK) return rc;
+        const int32_t n = *reinterpret_cast<int32_t*>(hr);
+        const int32_t* h_q = reinterpret_cast<int32_t*>(hr + 16);
+        if (out_q_host) memcpy(out_q_host, h_q, (size_t)n * 4);
+        if (out_t_host) memcpy(out_t_host, h_q + nq, (size_t)n * 4);
+        if (out_d_host) memcpy(out_d_host, h_q + 2 * nq, (size_t)n * 4);
+        *out_count_host = n;
+        return HM_OK;
+    }
     const size_t out_bytes = want_pts ? (size_t)(reinterpret_cast<uint8_t*>(d_pt + 2 * nq) - dr) : 16 + (size_t)nq * 12;
     GraphKey key;
     fill_key(&key, 1, nq, nt, flags, variant, want_pts ? 1 : 0, ratio_lut_host, dist_threshold);

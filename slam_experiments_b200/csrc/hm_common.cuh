@@ -283,6 +283,11 @@ int launch_gather_points(const int* q_idx, const int* t_idx, const int* count, l
                          const int* query_pts, long long nq, const int* train_pts, long long nt, int* out_query,
                          int* out_train, cudaStream_t stream);
 
+// single-launch small-problem pipeline (hm_small.cu)
+bool small_match_eligible(long long nq, long long nt);
+int launch_small_match(const uint8_t* q, long long nq, const uint8_t* t, long long nt, unsigned flags, const RatioLut& lut,
+                       int thr_ceil, int* out_mapped, unsigned epoch, cudaStream_t stream);
+
 // ORB descriptor stage (hm_orb.cu)
 size_t orb_workspace_bytes(int rows, int cols, int n_levels);
 int launch_orb_pyramid(const uint8_t* image, int rows, int cols, long long row_stride, int channels, int n_levels, void* ws,
