@@ -110,7 +110,7 @@ def measure(wl, steps, warmup, variant_arg="auto", n_arg=65536, cpu_seconds=10.0
         verified_what = f"{rows_chk.size} of {n} rows vs the C oracle"
         cpu_fn = lambda m: cv2.BFMatcher(cv2.NORM_HAMMING).knnMatch(q[:m], t, k=2)
         cpu_pairs = lambda m: float(m) * n
-        launches = 4 if variant in ("i8", "f4") else 2
+        launches = 2 if variant == "f4" else 3 if variant == "i8" else 2      # f4: train expansion + one k-NN launch (query expanded inside, splits merged inside)
         nq_k, nt_k = n, n
     elif wl == "c1":
         # BASELINE configs[0]: the reference's own bundled pair (1.png / 2.png, ORB 200 features as shipped in
@@ -182,7 +182,7 @@ def measure(wl, steps, warmup, variant_arg="auto", n_arg=65536, cpu_seconds=10.0
         ref = cv2.BFMatcher(cv2.NORM_HAMMING)
         cpu_fn = lambda k: [ref.match(frames[i + 1], frames[i]) for i in range(k)]
         cpu_pairs = lambda k: float(k) * 2000 * 2000
-        launches = 4 if variant in ("i8", "f4") else 2
+        launches = 2 if variant == "f4" else 3 if variant == "i8" else 2      # f4: train expansion + one k-NN launch (query expanded inside, splits merged inside)
         nq_k, nt_k = 2000, 2000
     else:  # c5
         qs, ts = synth.local_window(32, 10000)
