@@ -427,7 +427,8 @@ template <class C, int kMode, int kGroups = 4>
 __device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, Top2<typename C::Acc>& s)
 {
     using Acc = typename C::Acc;
-    Acc gm[4];
+    static_assert(kGroups == 2 || kGroups == 4 || kGroups == 8, "8-column groups per compare");
+    Acc gm[kGroups];
 #pragma unroll
     for (int g = 0; g < kGroups; ++g) {
         const int o = g * 8;
@@ -435,7 +436,10 @@ __device__ __forceinline__ void scan_chunk(const uint32_t* r, unsigned colbase, 
                         C::max3(C::from_bits(r[o + 3]), C::from_bits(r[o + 4]), C::from_bits(r[o + 5])),
                         C::max2(C::from_bits(r[o + 6]), C::from_bits(r[o + 7])));
     }
-    const Acc m = kGroups == 4 ? C::max3(gm[0], gm[1], C::max2(gm[2], gm[3])) : C::max2(gm[0], gm[1]);
+    Acc m;
+    if constexpr (kGroups == 8) m = C::max3(C::max3(gm[0], gm[1], gm[2]), C::max3(gm[3], gm[4], gm[5]), C::max2(gm[6], gm[7]));
+    else if constexpr (kGroups == 4) m = C::max3(gm[0], gm[1], C::max2(gm[2], gm[3]));
+    else m = C::max2(gm[0], gm[1]);
     constexpr bool kFloor = kMode == 1, kTop1 = kMode == 2;
     if (m > (kFloor ? s.f : kTop1 ? s.v1 : s.v2)) {
 #if HM_TC_TRACE
@@ -477,6 +481,14 @@ __device__ __forceinline__ void mask_tail(uint32_t* r, unsigned colbase, unsigne
     }
 }
 
+// 1: the epilogue thread that releases an accumulator unit is picked with elect.sync, 0: lane 0
+#ifndef HM_ARRIVE_ELECT
+#define HM_ARRIVE_ELECT 1
+#endif
+// 1: the kind::mxf4 epilogue scans its 64 columns with one compare + branch, 0: as two 32-column chunks
+#ifndef HM_SCAN_FLAT64
+#define HM_SCAN_FLAT64 0
+#endif
 // tiles of a CTA during which the shared row thresholds are refreshed every tile (every 16th afterwards)
 #ifndef HM_FLOOR_DENSE_TILES
 #define HM_FLOOR_DENSE_TILES 32
@@ -834,7 +846,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                 // the accumulator unit is in registers: release it before the scan
                 ptx::tc_fence_before();
                 __syncwarp();
-                if (lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
+                if (HM_ARRIVE_ELECT ? ptx::elect_one() : lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
                 if (colbase + kCols > limit) {            // last tile of the train set only
                     mask_tail<C, 32>(r0, colbase, limit);
                     mask_tail<C, 32>(r1, colbase + 32, limit);
@@ -855,7 +867,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
 #endif
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
+                    if (HM_ARRIVE_ELECT ? ptx::elect_one() : lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
 #if HM_TC_EXPERIMENT != 0
                     unit += 2;
                     if (unit >= kUnits) { unit -= kUnits; ++unit_use; }
@@ -866,8 +878,12 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     // 32-register buffers, the next item's first half loaded while this item's second half is
                     // scanned -- 882)
                     mask_tail<C, 64>(r, colbase, limit);
+#if HM_SCAN_FLAT64
+                    scan_chunk<C, kMode, 8>(r, colbase, s);          // one compare + branch per 64 columns
+#else
                     scan_chunk<C, kMode>(r, colbase, s);
                     scan_chunk<C, kMode>(r + 32, colbase + 32, s);
+#endif
                 } else if constexpr (kCols == 32) {
                     uint32_t r[32];
                     ptx::tmem_ld_32x32(taddr, r);
@@ -875,7 +891,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     asm volatile("tcgen05.wait::ld.sync.aligned;\n" : HM_R32(r) : : "memory");
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
+                    if (HM_ARRIVE_ELECT ? ptx::elect_one() : lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
                     mask_tail<C, 32>(r, colbase, limit);
                     scan_chunk<C, kMode>(r, colbase, s);
                 } else {
@@ -887,7 +903,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     tmem_ld_fence48(r0, r1);
                     ptx::tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
+                    if (HM_ARRIVE_ELECT ? ptx::elect_one() : lane == 0) ptx::mbar_arrive_addr(unit_empty_addr + unit * 8);
                     mask_tail<C, 32>(r0, colbase, limit);
                     mask_tail<C, 16>(r1, colbase + 32, limit);
                     scan_chunk<C, kMode>(r0, colbase, s);

@@ -9,6 +9,14 @@
 namespace hm {
 namespace ptx {
 
+// experiment knob: suspend-time hint (ns) of mbarrier.try_wait -- a waiting thread sleeps in hardware up to this long
+// before the instruction returns false, instead of coming back to spin
+#ifndef HM_TRYWAIT_HINT_NS
+#define HM_TRYWAIT_HINT_NS 0
+#endif
+#define HM_STR2(x) #x
+#define HM_STR(x) HM_STR2(x)
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
 {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -55,7 +63,11 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity)
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
+#if HM_TRYWAIT_HINT_NS
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, " HM_STR(HM_TRYWAIT_HINT_NS) ";\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+#endif
         "selp.b32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
@@ -71,7 +83,11 @@ __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar_addr, uint32_t p
     asm volatile(
         "{\n\t"
         ".reg .pred P;\n\t"
+#if HM_TRYWAIT_HINT_NS
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, " HM_STR(HM_TRYWAIT_HINT_NS) ";\n\t"
+#else
         "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+#endif
         "selp.b32 %0, 1, 0, P;\n\t"
         "}\n"
         : "=r"(ok)
