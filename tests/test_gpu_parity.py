@@ -479,3 +479,31 @@ def test_resident_database_packed_query(variant):
     q2 = rng.integers(0, 3, (513, 32), dtype=np.uint8)
     got = nat.knn2_keys_resident(dev(q2), nat.prepare(dev(t2), variant=variant), t2.shape[0], variant=variant)
     assert np.array_equal(got.cpu().numpy().view(np.uint64), co.knn2_keys(q2, t2))
+
+
+@pytest.mark.parametrize("variant", ("i8", "f4"))
+@pytest.mark.parametrize("nt", (200, 1000, 40001, 300000))
+def test_top2_at_group_tile_and_split_boundaries(variant, nt):
+    """The tensor-core scan keeps its top-2 at the granularity of 8-column groups and takes the exact top-2 from the
+    saved dots of two groups: plant the best and second-best train rows of every query at positions that stress it --
+    both in one group, in adjacent groups, across the 64-column halves of a tile, across tiles and splits, in the last
+    (ragged) rows, as exact duplicates (distance ties broken by index) and as near copies."""
+    rng = np.random.default_rng(nt)
+    t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+    pairs = [(0, 1), (6, 7), (7, 8), (63, 64), (127, 128), (120, 135), (nt - 2, nt - 1), (nt - 9, nt - 8), (5, nt - 1),
+             (nt // 2, nt // 2 + 1), (nt // 2 - 1, nt // 2 + 64), (3, 3)]
+    q = rng.integers(0, 256, (len(pairs) * 3, 32), dtype=np.uint8)
+    for i, (a, b) in enumerate(pairs):
+        base = q[3 * i].copy()
+        q[3 * i + 1], q[3 * i + 2] = base, base
+        t[a] = base                                   # distance 0
+        if b != a:
+            t[b] = base                               # an exact duplicate later: same distance, higher index
+        near = base.copy()
+        near[0] ^= 0x01
+        if a + 3 < nt and a + 3 != b:
+            t[a + 3] = near                           # distance 1 for the first two queries of the triple
+        q[3 * i + 2, 1] ^= 0x03                       # third query: distance 2 to both copies, 3 to the near copy
+    assert np.array_equal(gpu_keys(q, t, variant), co.knn2_keys(q, t))
+    big_q = np.concatenate([q, synth.matchable_queries(t, 700, 5)])
+    assert np.array_equal(gpu_keys(big_q, t, variant), co.knn2_keys(big_q, t))
