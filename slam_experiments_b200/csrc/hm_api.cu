@@ -800,6 +800,8 @@ HM_API int hm_knn2_host(hm_context* ctx, const uint8_t* query_host, int64_t nq, 
     const size_t kb = align_up((size_t)nq * 16, 1024);
     const size_t wsb = align_up(hm_workspace_bytes(nq, nt, 1, variant), 1024);
     const size_t dneed = qb + tb + kb + wsb, hneed = qb + tb + kb;
+    if (ctx->staged) HM_CUDA_CHECK(cudaEventSynchronize(ctx->staged));      // see ctx_reserve
+    if (ctx->d_cap < dneed || ctx->h_cap < hneed) HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
     if (ctx->d_cap < dneed) {
         if (ctx->d_buf) cudaFree(ctx->d_buf);
         ctx->d_buf = nullptr; ctx->d_cap = 0;
@@ -829,6 +831,8 @@ HM_API int hm_knn2_host(hm_context* ctx, const uint8_t* query_host, int64_t nq, 
 
 static int ctx_reserve(hm_context* ctx, size_t dneed, size_t hneed)
 {
+    // every caller is about to overwrite h_buf: an unsynchronised upload out of it (hm_frame_put_orb) must have left
+    if (ctx->staged) HM_CUDA_CHECK(cudaEventSynchronize(ctx->staged));
     if (ctx->d_cap < dneed || ctx->h_cap < hneed) HM_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));   // queued work may still use the old buffers
     if (ctx->d_cap < dneed) {
         if (ctx->d_buf) cudaFree(ctx->d_buf);
