@@ -487,7 +487,7 @@ __device__ __forceinline__ void mask_tail(uint32_t* r, unsigned colbase, unsigne
 #endif
 // 1: the kind::mxf4 epilogue scans its 64 columns with one compare + branch, 0: as two 32-column chunks
 #ifndef HM_SCAN_FLAT64
-#define HM_SCAN_FLAT64 0
+#define HM_SCAN_FLAT64 1
 #endif
 // tiles of a CTA during which the shared row thresholds are refreshed every tile (every 16th afterwards)
 #ifndef HM_FLOOR_DENSE_TILES
@@ -496,6 +496,15 @@ __device__ __forceinline__ void mask_tail(uint32_t* r, unsigned colbase, unsigne
 #ifndef HM_FLOOR_LATE_MASK
 #define HM_FLOOR_LATE_MASK 15
 #endif
+
+// 1 (kind::mxf4 only): the A operand (the CTA's 256 query rows) lives in tensor memory, 32 columns per 128-row block,
+// written once by the epilogue warps; the MMAs read only B from shared memory.  Halves the tensor core's
+// shared-memory operand traffic (A + B from shared memory is 128 B/clk/SM, the whole shared-memory bandwidth).
+#ifndef HM_F4_A_TMEM
+#define HM_F4_A_TMEM 1
+#endif
+constexpr int kATmemCol = 384;                       // [384, 448): after three 128-column accumulator units
+constexpr int kATmemColsPerBlock = 32;               // 256 e2m1 = 128 bytes per row
 
 // half `h` (0 / 1) of the MMAs of one (tile, query block) item: kSlabs * 2 instructions
 template <class C>
@@ -508,10 +517,15 @@ __device__ __forceinline__ void issue_half(int h, uint32_t a_block, uint32_t b_s
         const int j = h * kHalf + jj;
         const int slab = j >> 2, k = j & 3;
         // a_block / b_stage are descriptor start-address fields (shared-memory address >> 4)
-        const uint64_t da = ptx::kmajor_sw128_desc_from_lo(a_block + ((slab * kSlabBytes + k * 32) >> 4));
         const uint64_t db = ptx::kmajor_sw128_desc_from_lo(b_stage + ((slab * kSlabBytes + k * 32) >> 4));
-        if constexpr (C::kScales) ptx::mma_mxf4_ss(tmem_d, da, db, idesc, tmem_sf, tmem_sf + kScaleCols / 2, j != 0);
-        else                      ptx::mma_i8_ss(tmem_d, da, db, idesc, j != 0);
+        if constexpr (C::kScales && HM_F4_A_TMEM) {
+            // a_block is the TMEM address of the block's first A column; K = 64 elements = 8 columns per instruction
+            ptx::mma_mxf4_ts(tmem_d, a_block + 8 * j, db, idesc, tmem_sf, tmem_sf + kScaleCols / 2, j != 0);
+        } else {
+            const uint64_t da = ptx::kmajor_sw128_desc_from_lo(a_block + ((slab * kSlabBytes + k * 32) >> 4));
+            if constexpr (C::kScales) ptx::mma_mxf4_ss(tmem_d, da, db, idesc, tmem_sf, tmem_sf + kScaleCols / 2, j != 0);
+            else                      ptx::mma_i8_ss(tmem_d, da, db, idesc, j != 0);
+        }
     }
 }
 
@@ -615,7 +629,45 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
             ptx::tmem_st_32x32(taddr, ones);
             ptx::tmem_st_wait();
         }
-        if (P.qbits) {
+        if (HM_F4_A_TMEM) {
+            // A operand into tensor memory: thread = query row (TMEM lane), 32 words = the row's 256 e2m1 values in
+            // logical order; one tcgen05.st per (128-row block, lane quarter), by the warps of the lower column half
+            static_assert(!HM_F4_A_TMEM || C::kUnits * C::kTileN <= kATmemCol, "accumulator units overlap the A operand");
+            static_assert(!HM_F4_A_TMEM || kATmemCol + kMBlocks * kATmemColsPerBlock <= kScaleCol, "A operand overlaps the scale factors");
+            if (warp >= kFirstEpiWarp && warp < kFirstEpiWarp + 4 * kMBlocks) {
+                const int wq = warp & 3, wblk = ((warp - kFirstEpiWarp) >> 2) & 1;
+                const int r = wq * 32 + lane;
+                const long long qrow = (long long)qb * kBlockM + wblk * kRowBlock + r;
+                uint32_t words[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) words[i] = 0u;
+                if (qrow < rows_present()) {
+                    if (P.qbits) {
+                        const int* qidx = P.q_index ? P.q_index + (long long)b * P.q_index_batch_stride : nullptr;
+                        const long long srow = qidx ? (long long)__ldg(qidx + qrow) : qrow;
+                        const uint4* src = reinterpret_cast<const uint4*>(P.qbits + (long long)b * P.q_bits_batch_stride + srow * P.q_bits_stride);
+                        const uint4 lo = src[0], hi = src[1];
+                        const unsigned bits[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint4 v = expand_bits_e2m1(bits[c]);
+                            words[4 * c] = v.x; words[4 * c + 1] = v.y; words[4 * c + 2] = v.z; words[4 * c + 3] = v.w;
+                        }
+                    } else if (has_a) {
+                        // prepared image: 8-row atoms of 1024 bytes, logical 16-byte chunk c of row r at position c ^ (r & 7)
+                        const uint8_t* img = P.qprep + ((long long)b * P.q_padded + (long long)qb * kBlockM + wblk * kRowBlock) * C::kRowBytes;
+                        const uint4* row = reinterpret_cast<const uint4*>(img + (r >> 3) * 1024 + (r & 7) * 128);
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const uint4 v = row[c ^ (r & 7)];
+                            words[4 * c] = v.x; words[4 * c + 1] = v.y; words[4 * c + 2] = v.z; words[4 * c + 3] = v.w;
+                        }
+                    }
+                }
+                ptx::tmem_st_32x32(tmem_base + ((uint32_t)(wq * 32) << 16) + kATmemCol + wblk * kATmemColsPerBlock, words);
+                ptx::tmem_st_wait();
+            }
+        } else if (P.qbits) {
             // A operand from packed bits: the same swizzled image hm_prepare_f4_kernel writes, straight into shared
             // memory (chunk position -> row and logical chunk as there); rows past nq are +0.0 like the padding
             const uint8_t* qsrc = P.qbits + (long long)b * P.q_bits_batch_stride;
@@ -651,7 +703,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
     auto run_producer = [&]() {
         // ===== producer: bulk async copies global -> shared =====
         if (lane == 0) {
-            if (has_a && !P.qbits) {
+            if (has_a && !P.qbits && !(C::kScales && HM_F4_A_TMEM)) {
                 const uint8_t* qsrc = P.qprep + ((long long)b * P.q_padded + (long long)qb * kBlockM) * C::kRowBytes;
                 ptx::mbar_arrive_expect_tx(a_full_bar, kABytes);
                 ptx::bulk_g2s(smem_a, qsrc, kABytes, a_full_bar);       // two consecutive row blocks
@@ -693,10 +745,12 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
         // and blocking waits instead of the probes cost 70 cycles per tile.)
         const bool leader = ptx::elect_one();
         const uint32_t idesc = C::kScales ? ptx::make_mxf4_idesc(kRowBlock, kTileN) : ptx::make_i8_idesc(kRowBlock, kTileN);
-        const uint32_t a_addr = ptx::smem_u32(smem_a) >> 4;       // descriptor start-address fields
+        constexpr bool kATmem = C::kScales && HM_F4_A_TMEM;
+        const uint32_t a_addr = kATmem ? tmem_base + kATmemCol : ptx::smem_u32(smem_a) >> 4;       // TMEM address / descriptor start-address field
+        constexpr uint32_t kABlockStep = kATmem ? (uint32_t)kATmemColsPerBlock : (uint32_t)(kRowBlockBytes >> 4);
         const uint32_t b_addr = ptx::smem_u32(smem_b) >> 4;
         const uint32_t tmem_sf = tmem_base + kScaleCol;
-        if (has_a && !P.qbits) bounded_wait(a_full_bar, 0, P.error_flag);
+        if (has_a && !P.qbits && !(C::kScales && HM_F4_A_TMEM)) bounded_wait(a_full_bar, 0, P.error_flag);
         // The loop is unrolled over one period of the stage ring and of the unit rotation (kPeriod tiles), so that the
         // stage, the accumulator units, every barrier address, every descriptor offset and the unit parities are
         // compile-time constants: what is left per tile is the eight (sixteen) MMAs, three commits, the probes / waits
@@ -745,7 +799,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
                     if (!ready1) bounded_wait(&tmem_empty_bar[unit_b], par_b, P.error_flag);
                     if (leader) trace_mark(P, base + j, 6);           // second unit free
                     ptx::tc_fence_after();
-                    if (leader) issue_half<C>(0, a_addr + (kRowBlockBytes >> 4), b_stage, tmem_base + unit_b * kTileN, idesc, tmem_sf);
+                    if (leader) issue_half<C>(0, a_addr + kABlockStep, b_stage, tmem_base + unit_b * kTileN, idesc, tmem_sf);
                     ready0 = false;
                     if (base + j + 1 < my_tiles) {
                         const int n = j + 1;                       // n == kPeriod wraps to stage 0 / unit 0 of the next period
@@ -761,7 +815,7 @@ __device__ __forceinline__ void tc_knn2_body(const TcParams& P)
 #endif
                     }
                     if (leader) {
-                        issue_half<C>(1, a_addr + (kRowBlockBytes >> 4), b_stage, tmem_base + unit_b * kTileN, idesc, tmem_sf);
+                        issue_half<C>(1, a_addr + kABlockStep, b_stage, tmem_base + unit_b * kTileN, idesc, tmem_sf);
 #if HM_TC_EXPERIMENT == 6 || HM_COMMIT_MODE == 1
                         ptx::tc_commit(&tmem_full_bar[unit_a]);
 #endif

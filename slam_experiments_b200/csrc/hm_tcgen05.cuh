@@ -232,6 +232,21 @@ __device__ __forceinline__ void mma_mxf4_ss(uint32_t tmem_d, uint64_t desc_a, ui
         : "memory");
 }
 
+// the same with the A operand read from TENSOR MEMORY (lane = row, 8 e2m1 elements per 32-bit column, 8 columns per
+// K = 64 instruction): no shared-memory reads for A
+__device__ __forceinline__ void mma_mxf4_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t tmem_sfa, uint32_t tmem_sfb, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%6], p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+
 // 32 lanes x 32 consecutive 32-bit columns, registers -> TMEM (scale-factor fill)
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32])
 {
