@@ -1,8 +1,11 @@
+"""Development aid: thirty full-size launches against the C oracle (intermittent-hazard hunt).  python tools/repro_c4.py [keyframes]"""
 import sys, numpy as np, torch
 sys.path.insert(0,'/root/repo')
 from slam_experiments_b200 import _native as nat, synth
 from oracle import c_oracle as co
-q,t=synth.keyframe_database()
+nkf=int(sys.argv[1]) if len(sys.argv)>1 else 4096
+q,t=synth.keyframe_database(nkf)
+print('launch', nat.describe_launch(2000,t.shape[0],1,'f4'))
 exp=co.knn2_keys(q,t)
 td=torch.from_numpy(t).cuda(); qd=torch.from_numpy(q).cuda()
 tp=nat.prepare(td,variant='f4'); qp=nat.prepare(qd,variant='f4')
