@@ -15,7 +15,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 import torch
-from cv2 import KeyPoint, ORB
+from cv2 import KeyPoint, KeyPoint_convert, ORB
 
 from . import _native as nat
 
@@ -33,15 +33,14 @@ class FeatureDetector(ABC):
 
 
 def keypoint_arrays(keypoints: Sequence[KeyPoint]):
-    """``(xy float32 [n, 2], angle float32 [n], octave int32 [n])`` of a cv2 keypoint sequence."""
+    """``(xy float32 [n, 2], angle float32 [n], octave int32 [n])`` of a cv2 keypoint sequence (positions through
+    ``cv2.KeyPoint_convert``, one C++ call; the other two fields have no bulk accessor)."""
     n = len(keypoints)
-    xy = np.empty((n, 2), np.float32)
-    ang = np.empty(n, np.float32)
-    octv = np.empty(n, np.int32)
-    for i, k in enumerate(keypoints):
-        xy[i] = k.pt
-        ang[i] = k.angle
-        octv[i] = k.octave
+    if n == 0:
+        return np.empty((0, 2), np.float32), np.empty(0, np.float32), np.empty(0, np.int32)
+    xy = np.ascontiguousarray(KeyPoint_convert(keypoints), dtype=np.float32).reshape(n, 2)
+    ang = np.fromiter((k.angle for k in keypoints), np.float32, n)
+    octv = np.fromiter((k.octave for k in keypoints), np.int32, n)
     return xy, ang, octv
 
 
