@@ -16,9 +16,10 @@
 // elected thread issues the MMAs (M=128, N=128) into one of the 128-column TMEM accumulator units;
 // epilogue warps (kind::i8: eight, one per 32 query rows; kind::mxf4: sixteen, two column halves per
 // lane quarter) read finished units with tcgen05.ld (thread = query row, registers = train columns) and
-// keep the running top-2 in registers, so the distance tile never leaves the SM.  kind::i8 uses four
-// units (2 query blocks x 2 buffers = all 512 columns); kind::mxf4 rotates three units and keeps its
-// scale factors in the last 128 columns.  Three kernels per core: top-2, top-2 with row thresholds shared
+// keep the running top-2 in registers -- at the granularity of 8-column groups, see Top2 -- so the distance tile
+// never leaves the SM.  kind::i8 uses four units (2 query blocks x 2 buffers = all 512 columns); kind::mxf4 rotates
+// three units and keeps its scale factors in the last 32 columns; its CTA carries a fifth warpgroup that hands
+// registers to the epilogue warps (setmaxnreg, see threads()).  Three kernels per core: top-2, top-2 with row thresholds shared
 // by all CTAs of a query row (split launches), top-1 (passes whose second neighbour nobody reads).
 //
 // Why this shape (ncu, profiles/r01a_* .. r01g_*): the +/-1 operands are 8x (4x) larger than the
