@@ -874,7 +874,8 @@ static int small_match_run(hm_context* ctx, const uint8_t* q_dev, int64_t nq, co
     for (unsigned long long spins = 1;; ++spins) {
         if ((unsigned)vres[1] == epoch) break;
         if ((spins & 0x3FFF) == 0) {                  // the failure check: a kernel that died never publishes
-            const cudaError_t e = cudaStreamQuery(ctx->stream);
+            // after ~1 ms of polling the device is evidently busy with something else: stop burning the core
+            const cudaError_t e = spins > (1ull << 20) ? cudaStreamSynchronize(ctx->stream) : cudaStreamQuery(ctx->stream);
             if (e == cudaSuccess) {
                 if ((unsigned)vres[1] == epoch) break;
                 set_error("small-problem kernel finished without publishing its result");

@@ -18,6 +18,8 @@
 //     the host polls that word (bounded, with cudaStreamQuery as the failure check) instead of synchronising.
 #include <cooperative_groups.h>
 
+#include <mutex>
+
 #include "hm_common.cuh"
 
 namespace cg = cooperative_groups;
@@ -222,13 +224,17 @@ bool small_match_eligible(long long nq, long long nt)
 int launch_small_match(const uint8_t* q, long long nq, const uint8_t* t, long long nt, unsigned flags, const RatioLut& lut,
                        int thr_ceil, int* out_mapped, unsigned epoch, cudaStream_t stream)
 {
+    static std::mutex mu;                     // the > 48 KB opt-in is per device; one process may drive several
     static bool attr_done[64] = {};
     int dev = 0;
     HM_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        HM_CUDA_CHECK(cudaFuncSetAttribute(hm_small_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)small_smem_bytes(HM_SMALL_MAX_ROWS, HM_SMALL_MAX_ROWS)));
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+            HM_CUDA_CHECK(cudaFuncSetAttribute(hm_small_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (int)small_smem_bytes(HM_SMALL_MAX_ROWS, HM_SMALL_MAX_ROWS)));
+            if (dev >= 0 && dev < 64) attr_done[dev] = true;
+        }
     }
     SmallParams P{};
     P.q = reinterpret_cast<const uint4*>(q); P.t = reinterpret_cast<const uint4*>(t);
