@@ -1208,15 +1208,23 @@ int prologue_tiles()
     return v;
 }
 
+// clusters of 2 pay from this many tiles per CTA on (HM_CLUSTER_MIN_TILES overrides, for sweeps)
+int cluster_min_tiles()
+{
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("HM_CLUSTER_MIN_TILES");
+        v = e ? atoi(e) : 1024;
+    }
+    return v;
+}
+
 template <class C>
-TcPlan plan_tc(long long nq, long long nt, int batch, int sm_count)
+TcPlan plan_tc_cluster(long long nq, long long nt, int batch, int sm_count, int cluster)
 {
     TcPlan pl{};
     const long long qb = ceil_div(nq, kBlockM);
-    // pairs of query blocks share every train tile through multicast: half the L2 reads, +1.7 % on the
-    // power-capped C4 workload (6297 vs 6189 Gpairs/s); clusters of 4 lose SMs to GPC packing (6003)
-    pl.cluster = qb >= 2 ? 2 : 1;
-    if (cluster_override()) pl.cluster = cluster_override();
+    pl.cluster = cluster;
     pl.qblocks = ceil_div(qb, pl.cluster) * pl.cluster;
     sm_count = resident_ctas<C>(pl.cluster, sm_count);
     pl.ntiles = (int)ceil_div(nt, C::kTileN);
@@ -1239,6 +1247,21 @@ TcPlan plan_tc(long long nq, long long nt, int batch, int sm_count)
     pl.tiles_per_split = (int)ceil_div(pl.ntiles, best);
     pl.splits = (int)ceil_div(pl.ntiles, pl.tiles_per_split);
     return pl;
+}
+
+template <class C>
+TcPlan plan_tc(long long nq, long long nt, int batch, int sm_count)
+{
+    if (cluster_override()) return plan_tc_cluster<C>(nq, nt, batch, sm_count, cluster_override());
+    // Pairs of query blocks share every train tile through multicast: half the L2 reads, 1.7 % on C4 (690 vs 702 cycles
+    // per tile at 1730 tiles per CTA; clusters of 4 lose SMs to GPC packing: 747).  CTAs that see few tiles gain nothing
+    // from it and schedule better alone: C5 (79 tiles per CTA) +2 %, C2 (16) +2.5 %, 16k x 16k +2.5 %, and a wash for
+    // the 2000-query shards of the multi-GPU runs (445-889 tiles: within 0.7 %).
+    if (ceil_div(nq, kBlockM) >= 2) {
+        const TcPlan pl = plan_tc_cluster<C>(nq, nt, batch, sm_count, 2);
+        if (pl.tiles_per_split >= cluster_min_tiles()) return pl;
+    }
+    return plan_tc_cluster<C>(nq, nt, batch, sm_count, 1);
 }
 
 // rows of a prepared image: whole tiles of the core's height, rounded up to whole 256-row query blocks
