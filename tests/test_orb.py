@@ -230,3 +230,40 @@ def test_oracle_describe_on_the_references_own_inputs():
         meta = g["meta"][i, :n]
         got = oo.describe(noisy, g["points"][i, :n], meta[:, 1], meta[:, 2].astype(np.int32))
         assert np.array_equal(got, g["descriptors"][i, :n]), i
+
+
+def test_oracle_describe_random_keypoints_all_octaves():
+    """Hand-made keypoints at arbitrary sub-pixel positions, angles and octaves (cv2.ORB.compute takes them as given):
+    pins the coordinate rounding (pt * (1 / scale), half to even) and the rotation for angles the detector never emits."""
+    img = synth.textured_image(480, 640, 77)
+    rng = np.random.default_rng(0)
+    kps = []
+    for _ in range(400):
+        o = int(rng.integers(0, 8))
+        s = float(oo.level_scale(o))
+        r, c = oo.level_size(480, 640, o)
+        kps.append(cv2.KeyPoint(float(rng.uniform(31.5, c - 32.5)) * s, float(rng.uniform(31.5, r - 32.5)) * s, 31.0 * s,
+                                float(rng.uniform(0, 360)), 1.0, o))
+    kps.sort(key=lambda k: k.octave)
+    k2, d = cv2.ORB.create(nfeatures=1000).compute(img, kps)
+    assert len(k2) == len(kps)
+    assert np.array_equal(oo.describe(img, *kp_arrays(k2)), d)
+
+
+@gpu
+def test_device_describe_random_keypoints_all_octaves():
+    """The same hand-made keypoints through hm_orb_describe."""
+    img = synth.textured_image(480, 640, 77)
+    rng = np.random.default_rng(0)
+    xy = np.empty((400, 2), np.float32)
+    ang = rng.uniform(0, 360, 400).astype(np.float32)
+    octv = np.sort(rng.integers(0, 8, 400)).astype(np.int32)
+    for i, o in enumerate(octv):
+        s = float(oo.level_scale(int(o)))
+        r, c = oo.level_size(480, 640, int(o))
+        xy[i] = (float(rng.uniform(31.5, c - 32.5)) * s, float(rng.uniform(31.5, r - 32.5)) * s)
+    dev = torch.device("cuda")
+    ws = nat.orb_build_pyramid(torch.from_numpy(img).to(dev), 8)
+    out = nat.orb_describe(ws, img.shape[:2], 8, torch.from_numpy(xy).to(dev), torch.from_numpy(nat.orb_angles_to_cs(ang)).to(dev),
+                           torch.from_numpy(octv).to(dev))
+    assert np.array_equal(out.cpu().numpy(), oo.describe(img, xy, ang, octv))
