@@ -1,6 +1,6 @@
 """Development aid: thirty full-size launches against the C oracle (intermittent-hazard hunt).  python tools/repro_c4.py [keyframes]"""
-import sys, numpy as np, torch
-sys.path.insert(0,'/root/repo')
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from slam_experiments_b200 import _native as nat, synth
 from oracle import c_oracle as co
 nkf=int(sys.argv[1]) if len(sys.argv)>1 else 4096
