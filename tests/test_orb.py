@@ -59,7 +59,9 @@ def test_oracle_blur_equals_cv2_float_filter():
     assert np.array_equal(g.view(np.uint32), oo.GAUSS7.view(np.uint32))
     rng = np.random.default_rng(3)
     diff = total = 0
-    for h, w in ((480, 640), (400, 533), (231, 309), (134, 179), (300, 127), (64, 67)):
+    shapes = [(480, 640), (400, 533), (231, 309), (134, 179), (300, 127), (64, 67)]
+    shapes += [(int(rng.integers(120, 260)), w) for w in range(40, 170)]       # every residue of the vector bodies' widths
+    for h, w in shapes:
         img = rng.integers(0, 256, (h, w), dtype=np.uint8)
         ref = cv2.sepFilter2D(img, cv2.CV_8U, g, g, borderType=cv2.BORDER_REFLECT_101)
         got = oo.blur_float7(np.pad(img, 3, mode="reflect"), h, w)
