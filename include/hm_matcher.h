@@ -209,7 +209,11 @@ HM_API int hm_filter_matches(const uint64_t* fwd_keys, int64_t nq, const uint64_
                              void* stream);
 
 /* knn2 (+ the swapped pass when HM_FLAG_MUTUAL) + hm_filter_matches in one enqueue.
- * out_keys (fwd, [batch][nq][2]) may be NULL when the caller only wants the match list. */
+ * out_keys (fwd, [batch][nq][2]) may be NULL when the caller only wants the match list.
+ * With the kind::mxf4 core the forward k-NN kernel applies the ratio test to each row's final keys itself and marks the
+ * best train row of every survivor as a candidate; the swapped pass then runs over the candidate train rows only
+ * (gathered in-kernel from a device-side list, row count read on the device: nothing is synchronised with the host).
+ * Same result as the full swapped pass; the workspace of hm_workspace_bytes() includes the candidate tables. */
 HM_API int hm_match_fused(const uint8_t* query, int64_t nq, int64_t q_stride, int64_t q_batch_stride,
                           const uint8_t* train, int64_t nt, int64_t t_stride, int64_t t_batch_stride,
                           int batch, unsigned flags, const uint16_t* ratio_lut_host, double dist_threshold,
