@@ -155,3 +155,29 @@ def test_glue_oracle_mask_numpy_equals_cv2_rectangles():
             finally:
                 go.cv2 = saved
             assert np.array_equal(with_cv2, plain)
+
+
+def test_candidate_pass_is_the_mutual_check():
+    """The algorithm of hm_match_fused's kind::mxf4 path, restated on the oracle: ratio test first, the best train rows of
+    its survivors become CANDIDATES, and the swapped (train -> query) top-1 runs over the candidate rows only.  A match
+    (q, t) is mutual iff q is the best query of t, and only candidates are ever asked -- so the result equals the full
+    cross-check pipeline, on random, matchable and tie-heavy inputs, with and without the ratio test."""
+    rng = np.random.default_rng(42)
+    cases = [(rng.integers(0, 256, (90, 32), dtype=np.uint8), rng.integers(0, 256, (140, 32), dtype=np.uint8)),
+             (rng.integers(0, 3, (120, 32), dtype=np.uint8), rng.integers(0, 3, (77, 32), dtype=np.uint8))]
+    t = rng.integers(0, 256, (300, 32), dtype=np.uint8)
+    q = t[rng.integers(0, 300, 200)].copy()
+    q[:120] ^= np.packbits(rng.random((120, 256)) < 0.1, axis=1)
+    cases.append((q, t))
+    for q, t in cases:
+        for ratio in (None, 0.75, 0.9):
+            idx, dist = ho.knn(q, t, 2)
+            keep = np.ones(len(q), bool) if ratio is None else ho.ratio_test(idx, dist, ratio)
+            cand = np.unique(idx[keep, 0])                                   # candidate train rows
+            if len(cand):
+                bidx, _ = ho.knn(t[cand], q, 1)                              # best query of each candidate only
+                best_query = dict(zip(cand.tolist(), bidx[:, 0].tolist()))
+                keep &= np.array([best_query.get(int(idx[r, 0]), -1) == r for r in range(len(q))])
+            got = np.nonzero(keep)[0]
+            eq, et, ed = ho.pipeline(q, t, ratio, True)
+            assert np.array_equal(got, eq) and np.array_equal(idx[got, 0], et) and np.array_equal(dist[got, 0], ed)
