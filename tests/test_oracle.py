@@ -181,3 +181,34 @@ def test_candidate_pass_is_the_mutual_check():
             got = np.nonzero(keep)[0]
             eq, et, ed = ho.pipeline(q, t, ratio, True)
             assert np.array_equal(got, eq) and np.array_equal(idx[got, 0], et) and np.array_equal(dist[got, 0], ed)
+
+
+def test_group_level_top2_is_exact():
+    """The tensor-core scan's data structure, restated in numpy: keep the two 8-column groups with the largest maxima
+    (strict '>' in ascending order = earliest group on ties) and only THEIR dots; the exact (distance, index) top-2 of
+    those 16 columns is the row's top-2 with cv2's tie rule.  Random, tie-heavy and planted-duplicate rows, ragged ends."""
+    rng = np.random.default_rng(7)
+    for nt, low in ((8, 256), (13, 256), (64, 256), (1000, 256), (1000, 3), (517, 2)):
+        t = rng.integers(0, low, (nt, 32), dtype=np.uint8)
+        q = rng.integers(0, low, (40, 32), dtype=np.uint8)
+        q[:10] = t[rng.integers(0, nt, 10)]                               # exact duplicates: distance 0
+        if nt > 20:
+            t[nt - 1] = q[3]; t[7] = q[3]; t[8] = q[3]                     # ties across a group boundary and at the ragged end
+        D = ho.hamming_matrix(q, t).astype(np.int64)
+        dots = 256 - 2 * D
+        pad = (-nt) % 8
+        dots_p = np.concatenate([dots, np.full((len(q), pad), -10**6)], axis=1)     # masked tail (mask_tail in the kernel)
+        for r in range(len(q)):
+            v1 = v2 = -10**9
+            g1 = g2 = -1
+            for g in range(dots_p.shape[1] // 8):
+                x = dots_p[r, 8 * g:8 * g + 8].max()
+                if x > v2:
+                    if x > v1:
+                        v2, g2, v1, g1 = v1, g1, x, g
+                    else:
+                        v2, g2 = x, g
+            cols = [c for g in (g1, g2) if g >= 0 for c in range(8 * g, 8 * g + 8) if c < nt]
+            keys = sorted((int(D[r, c]), c) for c in cols)[:2]
+            exact = sorted((int(D[r, c]), c) for c in range(nt))[:2]
+            assert keys == exact, (nt, low, r)
